@@ -1,0 +1,720 @@
+/*
+ * pixflow_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, fp32, no FMA contraction) of the reference hot path of
+ * MungoMeng/Panorama-OpticalFlow: the PixFlow flow engine (CPU/PixFlow.hpp) and the
+ * novel-view prepare/combine functions (CPU/OpticalFlow.cpp).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ *
+ * Parity status: the reference cannot be compiled in this image (needs OpenCV C++, glog, gflags;
+ * see DESIGN.md) and ships no tests, so parity is pinned two ways instead:
+ *   (1) every OpenCV primitive restated here (section A below) is checked BIT-FOR-BIT against
+ *       the same-named cv2 4.13.0 function in scalar mode (cv2.setUseOptimized(False)) by
+ *       tests/test_oracle_vs_cv2.py -- OpenCV is the un-vendored third-party dependency the
+ *       reference calls (README.md:34 pins "OpenCV-3.20");
+ *   (2) the loops (section B) are transcriptions of the reference loops, each function citing
+ *       the file:line it follows, and the whole pipeline is cross-checked against a second,
+ *       independent composition of cv2 calls (oracle/cv2_oracle.py).
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile).  Never -march=native.
+ * All images are row-major and contiguous.  "c2" = 2 interleaved channels.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------ */
+/* Section A: OpenCV primitives (call sites: CPU/PixFlow.hpp:82-83,90-91,93-100,102-103,      */
+/* 123-124,128-134,147,284-294,307,325,338,390)                                               */
+/* ------------------------------------------------------------------------------------------ */
+
+static inline int clampi(int x, int a, int b) { return x < a ? a : (x > b ? b : x); }
+
+/* BORDER_REFLECT_101 index */
+static inline int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) {
+        if (p < 0) p = -p;
+        else p = 2 * n - 2 - p;
+    }
+    return p;
+}
+
+/* getGaussianKernel(k, sigma, CV_32F): float32(w_i / sum w), w in double */
+ORC_API void orc_gaussian_kernel(int k, double sigma, float* out) {
+    double w[64], s = 0;
+    for (int i = 0; i < k; ++i) {
+        double x = i - (k - 1) * 0.5;
+        w[i] = exp(-(x * x) / (2.0 * sigma * sigma));
+        s += w[i];
+    }
+    for (int i = 0; i < k; ++i) out[i] = (float)(w[i] / s);
+}
+
+/* GaussianBlur(src, dst, (k,k), sigma), fp32, ch interleaved channels, reflect-101.
+ * Row pass: k<=5 symmetric-small form, k>5 left-to-right; column pass symmetric form. */
+ORC_API void orc_gaussian_blur(const float* src, int h, int w, int ch, int k, double sigma, float* dst) {
+    float kern[64];
+    orc_gaussian_kernel(k, sigma, kern);
+    const int r = k / 2;
+    const size_t n = (size_t)h * w * ch;
+    float* tmp = (float*)malloc(n * sizeof(float));
+    for (int y = 0; y < h; ++y) {
+        const float* S = src + (size_t)y * w * ch;
+        float* D = tmp + (size_t)y * w * ch;
+        for (int x = 0; x < w; ++x) {
+            for (int c = 0; c < ch; ++c) {
+                float s0;
+                if (k <= 5) {
+                    s0 = S[x * ch + c] * kern[r];
+                    for (int i = 1; i <= r; ++i) {
+                        float a = S[reflect101(x - i, w) * ch + c];
+                        float b = S[reflect101(x + i, w) * ch + c];
+                        s0 = s0 + (a + b) * kern[r + i];
+                    }
+                } else {
+                    s0 = kern[0] * S[reflect101(x - r, w) * ch + c];
+                    for (int i = 1; i < k; ++i)
+                        s0 = s0 + kern[i] * S[reflect101(x - r + i, w) * ch + c];
+                }
+                D[x * ch + c] = s0;
+            }
+        }
+    }
+    const int wc = w * ch;
+    for (int y = 0; y < h; ++y) {
+        float* D = dst + (size_t)y * wc;
+        const float* C = tmp + (size_t)y * wc;
+        for (int x = 0; x < wc; ++x) {
+            float s0 = kern[r] * C[x] + 0.0f;
+            for (int i = 1; i <= r; ++i) {
+                float a = tmp[(size_t)reflect101(y + i, h) * wc + x];
+                float b = tmp[(size_t)reflect101(y - i, h) * wc + x];
+                s0 = s0 + kern[r + i] * (a + b);
+            }
+            D[x] = s0;
+        }
+    }
+    free(tmp);
+}
+
+/* Sobel(src, dst, -1, dx, dy, ksize=1, scale 1, delta 0, BORDER_REPLICATE): central difference */
+ORC_API void orc_sobel(const float* src, int h, int w, int dx, float* dst) {
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float a, b;
+            if (dx) {
+                a = src[(size_t)y * w + clampi(x + 1, 0, w - 1)];
+                b = src[(size_t)y * w + clampi(x - 1, 0, w - 1)];
+            } else {
+                a = src[(size_t)clampi(y + 1, 0, h - 1) * w + x];
+                b = src[(size_t)clampi(y - 1, 0, h - 1) * w + x];
+            }
+            dst[(size_t)y * w + x] = a - b;
+        }
+}
+
+static int cmp_float(const void* a, const void* b) {
+    float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+
+/* medianBlur(32FC2, 5): per-channel median of the replicated 5x5 window */
+ORC_API void orc_median5_c2(const float* src, int h, int w, float* dst) {
+    float v[25];
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            for (int c = 0; c < 2; ++c) {
+                int n = 0;
+                for (int dy = -2; dy <= 2; ++dy)
+                    for (int dx = -2; dx <= 2; ++dx)
+                        v[n++] = src[((size_t)clampi(y + dy, 0, h - 1) * w + clampi(x + dx, 0, w - 1)) * 2 + c];
+                /* partial selection sort up to the median */
+                for (int i = 0; i <= 12; ++i) {
+                    int m = i;
+                    for (int j = i + 1; j < 25; ++j)
+                        if (v[j] < v[m]) m = j;
+                    float t = v[i]; v[i] = v[m]; v[m] = t;
+                }
+                dst[((size_t)y * w + x) * 2 + c] = v[12];
+            }
+    (void)cmp_float;
+}
+
+/* cvtColor(BGRA2GRAY) u8, OpenCV 4.x 15-bit coefficients */
+ORC_API void orc_bgra2gray(const uint8_t* bgra, size_t npix, uint8_t* gray) {
+    for (size_t i = 0; i < npix; ++i) {
+        int B = bgra[4 * i], G = bgra[4 * i + 1], R = bgra[4 * i + 2];
+        gray[i] = (uint8_t)((B * 3735 + G * 19235 + R * 9798 + 16384) >> 15);
+    }
+}
+
+/* resize coordinate: f = float((d+0.5)*scale-0.5); s = floor(f); f -= s */
+static inline void resize_coord(int d, double scale, int* s, float* f) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    *s = sx;
+    *f = fx - (float)sx;
+}
+
+static inline void cubic_coeffs(float x, float* c) {
+    const float A = -0.75f;
+    c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+/* resize(..., INTER_LINEAR) fp32, ch channels */
+ORC_API void orc_resize_linear(const float* src, int sh, int sw, int ch, float* dst, int dh, int dw) {
+    const double scale_x = 1.0 / ((double)dw / (double)sw);
+    const double scale_y = 1.0 / ((double)dh / (double)sh);
+    int* xs = (int*)malloc(sizeof(int) * dw);
+    float* xf = (float*)malloc(sizeof(float) * dw);
+    for (int d = 0; d < dw; ++d) {
+        int s; float f;
+        resize_coord(d, scale_x, &s, &f);
+        if (s < 0) { s = 0; f = 0; }
+        if (s >= sw - 1) { s = sw - 1; f = 0; }
+        xs[d] = s; xf[d] = f;
+    }
+    float* r0 = (float*)malloc(sizeof(float) * dw * ch);
+    float* r1 = (float*)malloc(sizeof(float) * dw * ch);
+    for (int y = 0; y < dh; ++y) {
+        int sy; float fy;
+        resize_coord(y, scale_y, &sy, &fy);
+        /* rows are clamped, the fraction is NOT reset (OpenCV resizeGeneric_ row logic) */
+        int y0 = clampi(sy, 0, sh - 1), y1 = clampi(sy + 1, 0, sh - 1);
+        const float* S0 = src + (size_t)y0 * sw * ch;
+        const float* S1 = src + (size_t)y1 * sw * ch;
+        for (int d = 0; d < dw; ++d)
+            for (int c = 0; c < ch; ++c) {
+                int s = xs[d]; float f = xf[d];
+                if (s >= sw - 1) { /* dx >= xmax branch: D = S[sx]*1 */
+                    r0[d * ch + c] = S0[s * ch + c] * 1.0f;
+                    r1[d * ch + c] = S1[s * ch + c] * 1.0f;
+                } else {
+                    r0[d * ch + c] = S0[s * ch + c] * (1.f - f) + S0[(s + 1) * ch + c] * f;
+                    r1[d * ch + c] = S1[s * ch + c] * (1.f - f) + S1[(s + 1) * ch + c] * f;
+                }
+            }
+        const float b0 = 1.f - fy, b1 = fy;
+        float* D = dst + (size_t)y * dw * ch;
+        for (int i = 0; i < dw * ch; ++i) D[i] = r0[i] * b0 + r1[i] * b1;
+    }
+    free(xs); free(xf); free(r0); free(r1);
+}
+
+/* resize(..., INTER_CUBIC) fp32 with ch channels (used on the 2-channel flow).
+ * Vertical pass: right-to-left for the first n - n%4 floats of a row (4-lane baseline SIMD),
+ * left-to-right for the tail floats. */
+ORC_API void orc_resize_cubic_f32(const float* src, int sh, int sw, int ch, float* dst, int dh, int dw) {
+    const double scale_x = 1.0 / ((double)dw / (double)sw);
+    const double scale_y = 1.0 / ((double)dh / (double)sh);
+    int* xs = (int*)malloc(sizeof(int) * dw);
+    float* xc = (float*)malloc(sizeof(float) * dw * 4);
+    for (int d = 0; d < dw; ++d) {
+        float f;
+        resize_coord(d, scale_x, &xs[d], &f);
+        cubic_coeffs(f, xc + 4 * d);
+    }
+    const int n = dw * ch;
+    float* rows[4];
+    for (int k = 0; k < 4; ++k) rows[k] = (float*)malloc(sizeof(float) * n);
+    for (int y = 0; y < dh; ++y) {
+        int sy; float fy, b[4];
+        resize_coord(y, scale_y, &sy, &fy);
+        cubic_coeffs(fy, b);
+        for (int k = 0; k < 4; ++k) {
+            const float* S = src + (size_t)clampi(sy - 1 + k, 0, sh - 1) * sw * ch;
+            for (int d = 0; d < dw; ++d)
+                for (int c = 0; c < ch; ++c) {
+                    const float* a = xc + 4 * d;
+                    int s = xs[d];
+                    float v0 = S[clampi(s - 1, 0, sw - 1) * ch + c];
+                    float v1 = S[clampi(s, 0, sw - 1) * ch + c];
+                    float v2 = S[clampi(s + 1, 0, sw - 1) * ch + c];
+                    float v3 = S[clampi(s + 2, 0, sw - 1) * ch + c];
+                    rows[k][d * ch + c] = ((v0 * a[0] + v1 * a[1]) + v2 * a[2]) + v3 * a[3];
+                }
+        }
+        float* D = dst + (size_t)y * n;
+        const int nv = n - n % 4;
+        for (int i = 0; i < nv; ++i)
+            D[i] = ((rows[3][i] * b[3] + rows[2][i] * b[2]) + rows[1][i] * b[1]) + rows[0][i] * b[0];
+        for (int i = nv; i < n; ++i)
+            D[i] = ((rows[0][i] * b[0] + rows[1][i] * b[1]) + rows[2][i] * b[2]) + rows[3][i] * b[3];
+    }
+    for (int k = 0; k < 4; ++k) free(rows[k]);
+    free(xs); free(xc);
+}
+
+static inline short sat_short_rint(float v) {
+    long r = lrintf(v); /* round-half-even in the default rounding mode */
+    return (short)(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+}
+
+/* resize(..., INTER_CUBIC) on 8UC4: 11-bit fixed-point coefficients, integer horizontal pass,
+ * vertical pass float-based for the first n - n%8 bytes of a row, integer for the tail. */
+ORC_API void orc_resize_cubic_u8c4(const uint8_t* src, int sh, int sw, size_t sstride,
+                                   uint8_t* dst, int dh, int dw) {
+    const int ch = 4;
+    const double scale_x = 1.0 / ((double)dw / (double)sw);
+    const double scale_y = 1.0 / ((double)dh / (double)sh);
+    int* xs = (int*)malloc(sizeof(int) * dw);
+    short* xa = (short*)malloc(sizeof(short) * dw * 4);
+    for (int d = 0; d < dw; ++d) {
+        float f, c[4];
+        resize_coord(d, scale_x, &xs[d], &f);
+        cubic_coeffs(f, c);
+        for (int k = 0; k < 4; ++k) xa[4 * d + k] = sat_short_rint(c[k] * 2048.0f);
+    }
+    const int n = dw * ch;
+    int* rows[4];
+    for (int k = 0; k < 4; ++k) rows[k] = (int*)malloc(sizeof(int) * n);
+    for (int y = 0; y < dh; ++y) {
+        int sy; float fy, c[4];
+        short b[4];
+        resize_coord(y, scale_y, &sy, &fy);
+        cubic_coeffs(fy, c);
+        for (int k = 0; k < 4; ++k) b[k] = sat_short_rint(c[k] * 2048.0f);
+        for (int k = 0; k < 4; ++k) {
+            const uint8_t* S = src + (size_t)clampi(sy - 1 + k, 0, sh - 1) * sstride;
+            for (int d = 0; d < dw; ++d) {
+                const short* a = xa + 4 * d;
+                int s = xs[d];
+                int i0 = clampi(s - 1, 0, sw - 1) * ch, i1 = clampi(s, 0, sw - 1) * ch;
+                int i2 = clampi(s + 1, 0, sw - 1) * ch, i3 = clampi(s + 2, 0, sw - 1) * ch;
+                for (int cc = 0; cc < ch; ++cc)
+                    rows[k][d * ch + cc] = S[i0 + cc] * a[0] + S[i1 + cc] * a[1] + S[i2 + cc] * a[2] + S[i3 + cc] * a[3];
+            }
+        }
+        uint8_t* D = dst + (size_t)y * n;
+        const int nv = n - n % 8;
+        const float sc = 1.0f / 4194304.0f; /* 2^-22 */
+        const float b0 = (float)b[0] * sc, b1 = (float)b[1] * sc, b2 = (float)b[2] * sc, b3 = (float)b[3] * sc;
+        for (int i = 0; i < nv; ++i) {
+            float v = (((float)rows[3][i] * b3 + (float)rows[2][i] * b2) + (float)rows[1][i] * b1) + (float)rows[0][i] * b0;
+            long r = lrintf(v);
+            D[i] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+        }
+        for (int i = nv; i < n; ++i) {
+            int v = rows[0][i] * b[0] + rows[1][i] * b[1] + rows[2][i] * b[2] + rows[3][i] * b[3];
+            v = (v + (1 << 21)) >> 22;
+            D[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    for (int k = 0; k < 4; ++k) free(rows[k]);
+    free(xs); free(xa);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Section B: reference loops                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+
+/* PixFlow constants, CPU/PixFlow.hpp:32-44 and the factory presets :461-497 */
+#define K_PYR_MIN_IMAGE_SIZE 24
+#define K_GRAD_EPSILON 0.001f
+#define K_UPDATE_ALPHA_THRESHOLD 0.9f
+static const float kPyrScaleFactor = 0.9f;
+static const float kSmoothnessCoef = 0.001f;
+static const float kVerticalRegularizationCoef = 0.01f;
+static const float kHorizontalRegularizationCoef = 0.01f;
+static const float kGradientStepSize = 0.5f;
+static const float kDownscaleFactor = 0.5f;
+
+enum { HINT_UNKNOWN = 0, HINT_RIGHT = 1, HINT_DOWN = 2, HINT_LEFT = 3, HINT_UP = 4 }; /* PixFlow.hpp:19 */
+
+/* CPU/PixFlow.hpp:80-81 : Size(cols * 0.5f, rows * 0.5f) -> int truncation of an fp32 product */
+ORC_API void orc_downscale_size(int rows, int cols, int* dh, int* dw) {
+    *dw = (int)((float)cols * kDownscaleFactor);
+    *dh = (int)((float)rows * kDownscaleFactor);
+}
+
+/* CPU/PixFlow.hpp:137-151 buildPyramid sizes.  Returns the number of levels (>=1). */
+ORC_API int orc_pyramid_sizes(int w0, int h0, int* ws, int* hs, int cap) {
+    int n = 1;
+    ws[0] = w0; hs[0] = h0;
+    while (n < cap && n < 1000) {
+        int nw = (int)((float)ws[n - 1] * kPyrScaleFactor + 0.5f);
+        int nh = (int)((float)hs[n - 1] * kPyrScaleFactor + 0.5f);
+        if (nh <= K_PYR_MIN_IMAGE_SIZE || nw <= K_PYR_MIN_IMAGE_SIZE) break;
+        ws[n] = nw; hs[n] = nh;
+        ++n;
+    }
+    return n;
+}
+
+/* CPU/PixFlow.hpp:153-155 */
+ORC_API int orc_search_distance(int max_percentage) { return (K_PYR_MIN_IMAGE_SIZE * max_percentage + 50) / 100; }
+
+/* CPU/PixFlow.hpp:407-425 getPixBilinear32FExtend; img is one plane, row stride = w */
+static inline float pix_bilinear(const float* img, int w, int h, float x, float y) {
+    const float xm = (float)w - 2.0f, ym = (float)h - 2.0f;
+    { float t = (0.0f < x) ? x : 0.0f; x = (t < xm) ? t : xm; }   /* min(w-2, max(0,x)) with std:: semantics */
+    { float t = (0.0f < y) ? y : 0.0f; y = (t < ym) ? t : ym; }
+    const int x0 = (int)x, y0 = (int)y;
+    const float xR = x - (float)x0, yR = y - (float)y0;
+    const float* p = img + (size_t)y0 * w;
+    const float f00 = p[x0], f01 = p[x0 + w], f10 = p[x0 + 1], f11 = p[x0 + w + 1];
+    const float a1 = f00, a2 = f10 - f00, a3 = f01 - f00, a4 = f00 + f11 - f10 - f01;
+    return a1 + a2 * xR + a3 * yR + a4 * xR * yR;
+}
+
+typedef struct {
+    int w, h;
+    const float *I0x, *I0y, *I1x, *I1y; /* planes */
+    const float* blurred;               /* c2 */
+} SweepCtx;
+
+/* CPU/PixFlow.hpp:427-456 errorFunction */
+static inline float error_function(const SweepCtx* c, int x, int y, float fx, float fy) {
+    const float matchX = (float)x + fx, matchY = (float)y + fy;
+    const float i0x = c->I0x[(size_t)y * c->w + x], i0y = c->I0y[(size_t)y * c->w + x];
+    const float i1x = pix_bilinear(c->I1x, c->w, c->h, matchX, matchY);
+    const float i1y = pix_bilinear(c->I1y, c->w, c->h, matchX, matchY);
+    const float dX = c->blurred[((size_t)y * c->w + x) * 2] - fx;
+    const float dY = c->blurred[((size_t)y * c->w + x) * 2 + 1] - fy;
+    const float smoothness = sqrtf(dX * dX + dY * dY);
+    float err = sqrtf((i0x - i1x) * (i0x - i1x) + (i0y - i1y) * (i0y - i1y))
+              + smoothness * kSmoothnessCoef
+              + kVerticalRegularizationCoef * fabsf(fy) / (float)c->w
+              + kHorizontalRegularizationCoef * fabsf(fx) / (float)c->w;
+    return err;
+}
+
+/* one pixel of a sweep: CPU/PixFlow.hpp:317-322 (forward) / :330-335 (backward), with
+ * proposeFlowUpdate :342-362 and errorGradient :364-386 inlined */
+static inline void sweep_pixel(const SweepCtx* c, float* flow, int x, int y, int dir) {
+    const int w = c->w, h = c->h;
+    float* f = flow + ((size_t)y * w + x) * 2;
+    float currErr = error_function(c, x, y, f[0], f[1]);
+    const int hasX = dir > 0 ? (x > 0) : (x < w - 1);
+    const int hasY = dir > 0 ? (y > 0) : (y < h - 1);
+    if (hasX) {
+        const float* p = flow + ((size_t)y * w + (x - dir)) * 2;
+        const float px = p[0], py = p[1];
+        const float e = error_function(c, x, y, px, py);
+        if (e < currErr) { f[0] = px; f[1] = py; currErr = e; }
+    }
+    if (hasY) {
+        const float* p = flow + ((size_t)(y - dir) * w + x) * 2;
+        const float px = p[0], py = p[1];
+        const float e = error_function(c, x, y, px, py);
+        if (e < currErr) { f[0] = px; f[1] = py; currErr = e; }
+    }
+    const float ex = error_function(c, x, y, f[0] + K_GRAD_EPSILON, f[1] + 0.0f);
+    const float ey = error_function(c, x, y, f[0] + 0.0f, f[1] + K_GRAD_EPSILON);
+    const float gx = (ex - currErr) / K_GRAD_EPSILON, gy = (ey - currErr) / K_GRAD_EPSILON;
+    f[0] = f[0] - kGradientStepSize * gx;
+    f[1] = f[1] - kGradientStepSize * gy;
+}
+
+/* dir=+1: sweep from top/left (CPU/PixFlow.hpp:315-324); dir=-1: from bottom/right (:328-337).
+ * flow is updated in place; gradients are planes. */
+ORC_API void orc_sweep(const float* alpha0, const float* alpha1, const float* I0x, const float* I0y,
+                       const float* I1x, const float* I1y, const float* blurred, float* flow,
+                       int h, int w, int dir) {
+    SweepCtx c = { w, h, I0x, I0y, I1x, I1y, blurred };
+    if (dir > 0) {
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+                if (alpha0[(size_t)y * w + x] > K_UPDATE_ALPHA_THRESHOLD && alpha1[(size_t)y * w + x] > K_UPDATE_ALPHA_THRESHOLD)
+                    sweep_pixel(&c, flow, x, y, 1);
+    } else {
+        for (int y = h - 1; y >= 0; --y)
+            for (int x = w - 1; x >= 0; --x)
+                if (alpha0[(size_t)y * w + x] > K_UPDATE_ALPHA_THRESHOLD && alpha1[(size_t)y * w + x] > K_UPDATE_ALPHA_THRESHOLD)
+                    sweep_pixel(&c, flow, x, y, -1);
+    }
+}
+
+/* CPU/PixFlow.hpp:388-405 lowAlphaFlowDiffusion (blur + blend) */
+ORC_API void orc_low_alpha_diffusion(const float* alpha0, const float* alpha1, float* flow, int h, int w) {
+    float* bl = (float*)malloc(sizeof(float) * (size_t)h * w * 2);
+    orc_gaussian_blur(flow, h, w, 2, 15, 8.0, bl);
+    for (size_t i = 0; i < (size_t)h * w; ++i) {
+        const float d = 1.0f - alpha0[i] * alpha1[i];
+        flow[2 * i] = d * bl[2 * i] + (1.0f - d) * flow[2 * i];
+        flow[2 * i + 1] = d * bl[2 * i + 1] + (1.0f - d) * flow[2 * i + 1];
+    }
+    free(bl);
+}
+
+/* CPU/PixFlow.hpp:157-188 computePatchError */
+static float patch_error(const float* i0, const float* a0, int i0x, int i0y,
+                         const float* i1, const float* a1, int i1x, int i1y, int w, int h, int dist) {
+    float sad = 0, alpha = 0;
+    for (int dy = -2; dy <= 2; ++dy) {
+        const int d0y = i0y + dy;
+        if (0 <= d0y && d0y < h) {
+            const int d1y = clampi(i1y + dy, 0, h - 1);
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int d0x = i0x + dx;
+                if (0 <= d0x && d0x < w) {
+                    const int d1x = clampi(i1x + dx, 0, w - 1);
+                    const float difference = i0[(size_t)d0y * w + d0x] - i1[(size_t)d1y * w + d1x];
+                    sad += fabsf(difference);
+                    alpha += a0[(size_t)d0y * w + d0x] * a1[(size_t)d1y * w + d1x];
+                }
+            }
+        }
+    }
+    sad /= alpha;
+    /* norm(Point2f) is computed in double, then narrowed to float (:185) */
+    const float fx = (float)(i1x - i0x), fy = (float)(i1y - i0y);
+    const float length = (float)sqrt((double)fx * fx + (double)fy * fy);
+    sad *= 1 + length / dist;
+    return sad;
+}
+
+/* CPU/PixFlow.hpp:190-205 computeIntensityRatio: sequential fp32 sums */
+ORC_API float orc_intensity_ratio(const float* lhs, const float* la, const float* rhs, const float* ra, int h, int w) {
+    float sumLhs = 0, sumRhs = 0;
+    for (size_t i = 0; i < (size_t)h * w; ++i) {
+        const float alpha = la[i] * ra[i];
+        sumLhs += alpha * lhs[i];
+        sumRhs += alpha * rhs[i];
+    }
+    return sumLhs / sumRhs;
+}
+
+/* CPU/PixFlow.hpp:207-224 computeSearchBox -> (x, y, width, height); returns 0 on UNKNOWN */
+ORC_API int orc_search_box(int hint, int dist, int* box) {
+    const int ortho = (dist + 8 / 2) / 8, thickness = 2 * ortho + 1;
+    switch (hint) {
+    case HINT_RIGHT: box[0] = 0; box[1] = -ortho; box[2] = dist + 1; box[3] = thickness; return 1;
+    case HINT_DOWN: box[0] = -ortho; box[1] = 0; box[2] = thickness; box[3] = dist + 1; return 1;
+    case HINT_LEFT: box[0] = -dist; box[1] = -ortho; box[2] = dist + 1; box[3] = thickness; return 1;
+    case HINT_UP: box[0] = -ortho; box[1] = -dist; box[2] = thickness; box[3] = dist + 1; return 1;
+    default: return 0;
+    }
+}
+
+/* CPU/PixFlow.hpp:226-270 adjustInitialFlow; flow (c2, zero-initialised by the caller) */
+ORC_API void orc_adjust_initial_flow(const float* I0, const float* I1, const float* alpha0, const float* alpha1,
+                                     float* flow, int h, int w, int hint, int dist) {
+    const float ratio = orc_intensity_ratio(I0, alpha0, I1, alpha1, h, w);
+    float* I1eq = (float*)malloc(sizeof(float) * (size_t)h * w);
+    for (size_t i = 0; i < (size_t)h * w; ++i) I1eq[i] = I1[i] * ratio;
+    int box[4];
+    if (!orc_search_box(hint, dist, box)) { free(I1eq); return; }
+    for (int i0y = 0; i0y < h; ++i0y)
+        for (int i0x = 0; i0x < w; ++i0x)
+            if (alpha0[(size_t)i0y * w + i0x] > K_UPDATE_ALPHA_THRESHOLD) {
+                const float kFraction = 0.8f;
+                float errorBest = kFraction * patch_error(I0, alpha0, i0x, i0y, I1eq, alpha1, i0x, i0y, w, h, dist);
+                int i1xBest = i0x, i1yBest = i0y;
+                for (int dy = box[1]; dy < box[1] + box[3]; ++dy)
+                    for (int dx = box[0]; dx < box[0] + box[2]; ++dx) {
+                        const int i1x = i0x + dx, i1y = i0y + dy;
+                        if (0 <= i1x && i1x < w && 0 <= i1y && i1y < h) {
+                            const float error = patch_error(I0, alpha0, i0x, i0y, I1eq, alpha1, i1x, i1y, w, h, dist);
+                            if (errorBest > error) { errorBest = error; i1xBest = i1x; i1yBest = i1y; }
+                        }
+                    }
+                flow[((size_t)i0y * w + i0x) * 2] = (float)(i1xBest - i0x);
+                flow[((size_t)i0y * w + i0x) * 2 + 1] = (float)(i1yBest - i0y);
+            }
+    free(I1eq);
+}
+
+/* front end of computeOpticalFlow, CPU/PixFlow.hpp:78-103: cubic 1/2 downscale, gray + alpha,
+ * /255, 5x5 sigma 0.25 pre-blur (grey only).  I and A are (dh x dw) planes. */
+ORC_API void orc_frontend(const uint8_t* bgra, int rows, int cols, size_t stride, float* I, float* A) {
+    int dh, dw;
+    orc_downscale_size(rows, cols, &dh, &dw);
+    const size_t n = (size_t)dh * dw;
+    uint8_t* small = (uint8_t*)malloc(n * 4);
+    uint8_t* gray = (uint8_t*)malloc(n);
+    orc_resize_cubic_u8c4(bgra, rows, cols, stride, small, dh, dw);
+    orc_bgra2gray(small, n, gray);
+    const float inv255 = (float)(1.0 / 255.0); /* Mat /= 255.0f -> convertTo(alpha = 1/255.) */
+    float* g = (float*)malloc(n * sizeof(float));
+    for (size_t i = 0; i < n; ++i) {
+        g[i] = (float)gray[i] * inv255;
+        A[i] = (float)small[4 * i + 3] * inv255;
+    }
+    orc_gaussian_blur(g, dh, dw, 1, 5, 0.25, I);
+    free(small); free(gray); free(g);
+}
+
+/* optional per-level trace for tests: called after each stage with a stage id
+ * 0 blurredFlow, 1 after fwd sweep, 2 after median, 3 after bwd sweep, 4 after median,
+ * 5 after diffusion, 6 flow entering the level (after init/search or upsample) */
+typedef void (*orc_trace_fn)(void* user, int level, int stage, const float* data, int h, int w, int ch);
+
+/* one pyramid level, CPU/PixFlow.hpp:272-340.  flow: in/out (c2); first=1 when flow.empty() */
+ORC_API void orc_level(const float* I0, const float* I1, const float* a0, const float* a1, float* flow,
+                       int h, int w, int first, int hint, int max_percentage,
+                       orc_trace_fn trace, void* user, int level) {
+    const size_t n = (size_t)h * w;
+    float* g[4];
+    for (int k = 0; k < 4; ++k) g[k] = (float*)malloc(n * sizeof(float));
+    float* t = (float*)malloc(n * sizeof(float));
+    orc_sobel(I0, h, w, 1, t); orc_gaussian_blur(t, h, w, 1, 3, 0.5, g[0]);
+    orc_sobel(I0, h, w, 0, t); orc_gaussian_blur(t, h, w, 1, 3, 0.5, g[1]);
+    orc_sobel(I1, h, w, 1, t); orc_gaussian_blur(t, h, w, 1, 3, 0.5, g[2]);
+    orc_sobel(I1, h, w, 0, t); orc_gaussian_blur(t, h, w, 1, 3, 0.5, g[3]);
+    free(t);
+    if (first) {
+        memset(flow, 0, n * 2 * sizeof(float));
+        if (max_percentage > 0 && hint != HINT_UNKNOWN)
+            orc_adjust_initial_flow(I0, I1, a0, a1, flow, h, w, hint, orc_search_distance(max_percentage));
+    }
+    if (trace) trace(user, level, 6, flow, h, w, 2);
+    float* blurred = (float*)malloc(n * 2 * sizeof(float));
+    float* med = (float*)malloc(n * 2 * sizeof(float));
+    orc_gaussian_blur(flow, h, w, 2, 15, 8.0, blurred);
+    if (trace) trace(user, level, 0, blurred, h, w, 2);
+    orc_sweep(a0, a1, g[0], g[1], g[2], g[3], blurred, flow, h, w, +1);
+    if (trace) trace(user, level, 1, flow, h, w, 2);
+    orc_median5_c2(flow, h, w, med);
+    memcpy(flow, med, n * 2 * sizeof(float));
+    if (trace) trace(user, level, 2, flow, h, w, 2);
+    orc_sweep(a0, a1, g[0], g[1], g[2], g[3], blurred, flow, h, w, -1);
+    if (trace) trace(user, level, 3, flow, h, w, 2);
+    orc_median5_c2(flow, h, w, med);
+    memcpy(flow, med, n * 2 * sizeof(float));
+    if (trace) trace(user, level, 4, flow, h, w, 2);
+    orc_low_alpha_diffusion(a0, a1, flow, h, w);
+    if (trace) trace(user, level, 5, flow, h, w, 2);
+    free(blurred); free(med);
+    for (int k = 0; k < 4; ++k) free(g[k]);
+}
+
+/* PixFlow<MaxPercentage>::computeOpticalFlow, CPU/PixFlow.hpp:72-135.
+ * i0/i1: BGRA8 rows x cols with byte strides; flow_out: rows x cols x 2 floats. Returns 0. */
+ORC_API int orc_compute_flow(const uint8_t* i0, size_t stride0, const uint8_t* i1, size_t stride1,
+                             int rows, int cols, int max_percentage, int hint, float* flow_out,
+                             orc_trace_fn trace, void* user) {
+    int dh, dw;
+    orc_downscale_size(rows, cols, &dh, &dw);
+    int ws[128], hs[128];
+    const int L = orc_pyramid_sizes(dw, dh, ws, hs, 128);
+    float **P[4]; /* I0, I1, a0, a1 pyramids */
+    for (int k = 0; k < 4; ++k) {
+        P[k] = (float**)malloc(sizeof(float*) * L);
+        for (int l = 0; l < L; ++l) P[k][l] = (float*)malloc(sizeof(float) * (size_t)ws[l] * hs[l]);
+    }
+    orc_frontend(i0, rows, cols, stride0, P[0][0], P[2][0]);
+    orc_frontend(i1, rows, cols, stride1, P[1][0], P[3][0]);
+    for (int k = 0; k < 4; ++k)
+        for (int l = 1; l < L; ++l)
+            orc_resize_linear(P[k][l - 1], hs[l - 1], ws[l - 1], 1, P[k][l], hs[l], ws[l]);
+
+    float* flow = (float*)malloc(sizeof(float) * (size_t)ws[L - 1] * hs[L - 1] * 2);
+    const float upscale = 1.0f / kPyrScaleFactor;
+    for (int l = L - 1; l >= 0; --l) {
+        orc_level(P[0][l], P[1][l], P[2][l], P[3][l], flow, hs[l], ws[l], l == L - 1, hint, max_percentage, trace, user, l);
+        if (l > 0) {
+            const size_t nn = (size_t)ws[l - 1] * hs[l - 1] * 2;
+            float* up = (float*)malloc(sizeof(float) * nn);
+            orc_resize_cubic_f32(flow, hs[l], ws[l], 2, up, hs[l - 1], ws[l - 1]);
+            for (size_t i = 0; i < nn; ++i) up[i] = up[i] * upscale;
+            free(flow);
+            flow = up;
+        }
+    }
+    {
+        const size_t nn = (size_t)rows * cols * 2;
+        float* up = (float*)malloc(sizeof(float) * nn);
+        orc_resize_linear(flow, dh, dw, 2, up, rows, cols);
+        const float s = 1.0f / kDownscaleFactor;
+        for (size_t i = 0; i < nn; ++i) up[i] = up[i] * s;
+        orc_gaussian_blur(up, rows, cols, 2, 3, 1.0, flow_out);
+        free(up);
+    }
+    free(flow);
+    for (int k = 0; k < 4; ++k) {
+        for (int l = 0; l < L; ++l) free(P[k][l]);
+        free(P[k]);
+    }
+    return 0;
+}
+
+/* NovelViewGeneratorAsymmetricFlow::prepare, CPU/OpticalFlow.cpp:102-145: circular pad by
+ * cols/20, flow(L,R,LEFT), flow(R,L,RIGHT), crop.  Outputs rows x cols x 2 floats each. */
+ORC_API int orc_prepare_bidirectional(const uint8_t* L, size_t strideL, const uint8_t* R, size_t strideR,
+                                      int rows, int cols, int max_percentage, float* flowLR, float* flowRL) {
+    const int len = cols / 20, pc = cols + 2 * len;
+    uint8_t* pad[2];
+    const uint8_t* src[2] = { L, R };
+    const size_t st[2] = { strideL, strideR };
+    for (int k = 0; k < 2; ++k) {
+        pad[k] = (uint8_t*)malloc((size_t)rows * pc * 4);
+        for (int y = 0; y < rows; ++y) {
+            const uint8_t* s = src[k] + (size_t)y * st[k];
+            uint8_t* d = pad[k] + (size_t)y * pc * 4;
+            memcpy(d, s + (size_t)(cols - len) * 4, (size_t)len * 4);
+            memcpy(d + (size_t)len * 4, s, (size_t)cols * 4);
+            memcpy(d + (size_t)(len + cols) * 4, s, (size_t)len * 4);
+        }
+    }
+    float* f = (float*)malloc(sizeof(float) * (size_t)rows * pc * 2);
+    for (int dirn = 0; dirn < 2; ++dirn) {
+        if (dirn == 0) orc_compute_flow(pad[0], (size_t)pc * 4, pad[1], (size_t)pc * 4, rows, pc, max_percentage, HINT_LEFT, f, 0, 0);
+        else orc_compute_flow(pad[1], (size_t)pc * 4, pad[0], (size_t)pc * 4, rows, pc, max_percentage, HINT_RIGHT, f, 0, 0);
+        float* out = dirn == 0 ? flowLR : flowRL;
+        for (int y = 0; y < rows; ++y)
+            memcpy(out + (size_t)y * cols * 2, f + ((size_t)y * pc + len) * 2, sizeof(float) * (size_t)cols * 2);
+    }
+    free(f); free(pad[0]); free(pad[1]);
+    return 0;
+}
+
+/* NovelViewUtil::generateNovelViewPoint, CPU/OpticalFlow.cpp:9-28 */
+static inline const uint8_t* novel_view_point(const uint8_t* img, size_t stride, const float* flow,
+                                              double t, int x, int y, int rows, int cols) {
+    const float fx = flow[((size_t)y * cols + x) * 2], fy = flow[((size_t)y * cols + x) * 2 + 1];
+    int srcx = (int)(x + fx * t);
+    if (srcx > cols - 1) srcx = srcx - cols;
+    if (srcx < 0) srcx = srcx + cols;
+    int srcy = (int)(y + fy * t);
+    if (srcy > rows - 1) srcy = rows - 1;
+    if (srcy < 0) srcy = 0;
+    return img + (size_t)srcy * stride + (size_t)srcx * 4;
+}
+
+static inline float lerpf(float x0, float x1, float a) { return x0 * (1.0f - a) + x1 * a; } /* util.hpp:98-101 */
+
+/* NovelViewUtil::combineNovelViews, CPU/OpticalFlow.cpp:30-92. out: rows x cols BGRA8 contiguous */
+ORC_API int orc_combine_novel_views(const uint8_t* imageL, size_t strideL, const uint8_t* imageR, size_t strideR,
+                                    const float* flowLtoR, const float* flowRtoL, const float* blend,
+                                    int rows, int cols, uint8_t* out) {
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const float blendR = blend[(size_t)y * cols + x];
+            const float blendL = 1 - blendR;
+            const uint8_t* colorL = novel_view_point(imageL, strideL, flowRtoL, blendR, x, y, rows, cols);
+            const uint8_t* colorR = novel_view_point(imageR, strideR, flowLtoR, blendL, x, y, rows, cols);
+            uint8_t* o = out + ((size_t)y * cols + x) * 4;
+            if (colorL[3] == 0 || colorR[3] == 0) {
+                o[0] = o[1] = o[2] = o[3] = 0;
+            } else {
+                const float* fLR = flowLtoR + ((size_t)y * cols + x) * 2;
+                const float* fRL = flowRtoL + ((size_t)y * cols + x) * 2;
+                const float kColorDiffCoef = 10.0f, kSoftmaxSharpness = 10.0f, kFlowMagCoef = 100.0f;
+                const float flowMagLR = sqrtf(fLR[0] * fLR[0] + fLR[1] * fLR[1]) / (float)cols;
+                const float flowMagRL = sqrtf(fRL[0] * fRL[0] + fRL[1] * fRL[1]) / (float)cols;
+                const float colorDiff = (float)(abs(colorL[0] - colorR[0]) + abs(colorL[1] - colorR[1]) + abs(colorL[2] - colorR[2])) / 255.0f;
+                const float deghostCoef = tanhf(colorDiff * kColorDiffCoef);
+                const float alphaL = colorL[3] / 255.0f, alphaR = colorR[3] / 255.0f;
+                const double expL = exp(kSoftmaxSharpness * blendL * alphaL * (1.0 + kFlowMagCoef * flowMagRL));
+                const double expR = exp(kSoftmaxSharpness * blendR * alphaR * (1.0 + kFlowMagCoef * flowMagLR));
+                const double sumExp = expL + expR + 0.00001;
+                const float softmaxL = (float)(expL / sumExp), softmaxR = (float)(expR / sumExp);
+                const float wL = lerpf(blendL, softmaxL, deghostCoef), wR = lerpf(blendR, softmaxR, deghostCoef);
+                for (int c = 0; c < 3; ++c) {
+                    const float v = (float)colorL[c] * wL + (float)colorR[c] * wR;
+                    /* Vec4b(uchar,...) constructor args: implicit float -> uchar = truncation (:82-86) */
+                    o[c] = (uint8_t)(int)v;
+                }
+                o[3] = 255;
+            }
+        }
+    return 0;
+}
