@@ -1,0 +1,130 @@
+/*
+ * pixflow_b200.h -- C-ABI of libpixflow_b200.so: the B200-native (sm_100a) replacement for the flow /
+ * novel-view hot path of MungoMeng/Panorama-OpticalFlow.
+ *
+ * Every entry point names the reference interface it replaces (file:line under the reference tree).
+ * Conventions: plain pointers and sizes, int return codes (0 = PF_OK), no exceptions cross the ABI,
+ * caller-owned buffers.  Image pointers may be HOST or DEVICE pointers (detected with
+ * cudaPointerGetAttributes); strides are in BYTES.  Images are 8-bit BGRA (CV_8UC4), flows are
+ * interleaved (dx, dy) fp32 (CV_32FC2) in input-resolution pixels, blend is fp32 (CV_32FC1).
+ * All calls are synchronous (results are complete on return) unless stated otherwise.
+ * A CUDA device is mandatory: there is no CPU fallback -- engine creation fails with PF_ERR_NO_DEVICE.
+ */
+#ifndef PIXFLOW_B200_H
+#define PIXFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_API __attribute__((visibility("default")))
+
+enum pf_status {
+    PF_OK = 0,
+    PF_ERR_INVALID_ARGUMENT = 1,
+    PF_ERR_UNKNOWN_ALGORITHM = 2, /* reference: throw VrCamException("unrecognized flow algorithm name"), CPU/PixFlow.hpp:499 */
+    PF_ERR_CUDA = 3,
+    PF_ERR_NO_DEVICE = 4
+};
+
+/* OpticalFlowInterface::DirectionHint, CPU/PixFlow.hpp:19 (same numeric values as the enum class) */
+enum pf_direction_hint { PF_HINT_UNKNOWN = 0, PF_HINT_RIGHT = 1, PF_HINT_DOWN = 2, PF_HINT_LEFT = 3, PF_HINT_UP = 4 };
+
+typedef struct pf_engine pf_engine;
+
+/* Replaces makeOpticalFlowByName (CPU/PixFlow.hpp:459-500; GPU twin makeOpticalFlowByName_GPU,
+ * GPU/PixFlow_GPU.hpp) plus the device probe of GPU/OpticalFlow.cpp:132-171.
+ * flow_alg_name: "pixflow_low" (PixFlow<0>) or "pixflow_search_20" (PixFlow<20>); anything else ->
+ * PF_ERR_UNKNOWN_ALGORITHM.  device < 0 selects the current CUDA device. */
+PF_API int pf_engine_create(const char* flow_alg_name, int device, pf_engine** out_engine);
+/* Replaces `delete flowAlg` (CPU/OpticalFlow.cpp:141). */
+PF_API void pf_engine_destroy(pf_engine* engine);
+
+/* Replaces OpticalFlowInterface::computeOpticalFlow(I0BGRA, I1BGRA, flow, hint), CPU/PixFlow.hpp:21-25 and
+ * :72-135.  flow_out: rows x cols x (dx,dy) fp32. */
+PF_API int pf_compute_flow(pf_engine* engine,
+                           const void* i0_bgra, size_t i0_stride,
+                           const void* i1_bgra, size_t i1_stride,
+                           int rows, int cols, int hint,
+                           void* flow_out, size_t flow_stride);
+
+/* Replaces NovelViewGeneratorAsymmetricFlow::prepare(colorImageL, colorImageR), CPU/OpticalFlow.cpp:102-145:
+ * circular pad by cols/20, flow(L,R,LEFT) and flow(R,L,RIGHT) (both directions run concurrently), crop.
+ * Outputs the fields returned by getFlowLtoR()/getFlowRtoL() (CPU/OpticalFlow.hpp:67-68). */
+PF_API int pf_prepare_bidirectional(pf_engine* engine,
+                                    const void* image_l, size_t stride_l,
+                                    const void* image_r, size_t stride_r,
+                                    int rows, int cols,
+                                    void* flow_l_to_r, size_t stride_lr,
+                                    void* flow_r_to_l, size_t stride_rl);
+
+/* Batched form of pf_prepare_bidirectional for n independent overlap pairs of identical size (the replica /
+ * farm mode of SURVEY.md section 8e): all 2n flow computations are in flight concurrently on one device.
+ * Each array holds n pointers; all pairs share rows, cols and the stride of their kind. */
+PF_API int pf_prepare_bidirectional_batch(pf_engine* engine, int n,
+                                          const void* const* images_l, size_t stride_l,
+                                          const void* const* images_r, size_t stride_r,
+                                          int rows, int cols,
+                                          void* const* flows_l_to_r, size_t stride_lr,
+                                          void* const* flows_r_to_l, size_t stride_rl);
+
+/* Replaces NovelViewUtil::combineNovelViews(imageL, imageR, flowLtoR, flowRtoL, blend),
+ * CPU/OpticalFlow.cpp:30-92 (generateNovelViewPoint :9-28 inlined).  out_bgra: rows x cols BGRA8. */
+PF_API int pf_combine_novel_views(pf_engine* engine,
+                                  const void* image_l, size_t stride_l,
+                                  const void* image_r, size_t stride_r,
+                                  const void* flow_l_to_r, size_t stride_lr,
+                                  const void* flow_r_to_l, size_t stride_rl,
+                                  const void* blend, size_t stride_blend,
+                                  int rows, int cols,
+                                  void* out_bgra, size_t stride_out);
+
+/* Fused prepare + setBlend + generateNovelView (CPU/main.cpp:82-89): the flows stay in HBM, only the merged
+ * BGRA image is produced.  flow outputs may be NULL. */
+PF_API int pf_novel_view(pf_engine* engine,
+                         const void* image_l, size_t stride_l,
+                         const void* image_r, size_t stride_r,
+                         const void* blend, size_t stride_blend,
+                         int rows, int cols,
+                         void* out_bgra, size_t stride_out,
+                         void* flow_l_to_r, size_t stride_lr,
+                         void* flow_r_to_l, size_t stride_rl);
+
+/* Pinned host memory for zero-staging transfers (optional; any host pointer is accepted by the calls above). */
+PF_API int pf_host_alloc(void** ptr, size_t bytes);
+PF_API int pf_host_free(void* ptr);
+
+/* Number of kernel launches issued by this library so far in the process (bench.py's gpu_launches). */
+PF_API uint64_t pf_kernel_launch_count(void);
+/* Device time, in milliseconds, spent inside the wavefront sweep kernels during the last call on `engine`
+ * (CUDA events on the launching streams; 0 if timing is disabled).  pf_set_sweep_timing(engine, 1) enables. */
+PF_API int pf_set_sweep_timing(pf_engine* engine, int enabled);
+PF_API double pf_last_sweep_ms(pf_engine* engine);
+PF_API uint64_t pf_last_sweep_launches(pf_engine* engine);
+
+/* Message of the last error on the calling thread ("" if none).  Replaces exception::what(). */
+PF_API const char* pf_last_error(void);
+PF_API const char* pf_version(void);
+
+/* ---- diagnostic single-stage entry points (HOST pointers, contiguous arrays) --------------------------------
+ * One kernel each, used by tests/ to localise a divergence to a stage.  Not a product API. */
+PF_API int pf_stage_frontend(const void* bgra, int rows, int cols, int pad, float* grey, float* alpha, int dh, int dw);
+PF_API int pf_stage_gauss5(const float* src, float* dst, int h, int w);
+PF_API int pf_stage_pyr_down(const float* src, int sh, int sw, float* dst, int dh, int dw);
+PF_API int pf_stage_gradient(const float* I, float* G_interleaved, int h, int w);
+PF_API int pf_stage_blur15(const float* flow, float* dst, int h, int w, const float* alpha0, const float* alpha1);
+PF_API int pf_stage_median5(const float* flow, float* dst, int h, int w);
+PF_API int pf_stage_sweep(const float* alpha0, const float* alpha1, const float* G0, const float* G1,
+                          const float* blurred, float* flow_inout, int h, int w, int dir);
+PF_API int pf_stage_upsample_cubic(const float* src, int sh, int sw, float* dst, int dh, int dw);
+PF_API int pf_stage_tail(const float* flow0, int sh, int sw, int rows, int pcols, int pad, int cols, float* out);
+PF_API int pf_stage_initial_flow(const float* I0, const float* I1, const float* alpha0, const float* alpha1,
+                                 float* flow, int h, int w, int hint, int dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXFLOW_B200_H */

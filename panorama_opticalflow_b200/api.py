@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference's operator interface for the flow / novel-view path, over the C-ABI.
+
+Same names, argument meaning and error behaviour as the reference (C++ names kept on purpose):
+  OpticalFlowInterface / DirectionHint / makeOpticalFlowByName      CPU/PixFlow.hpp:15-26, :459-500
+  NovelViewUtil.combineNovelViews                                    CPU/OpticalFlow.hpp:26-31
+  NovelViewGenerator / NovelViewGeneratorAsymmetricFlow              CPU/OpticalFlow.hpp:34-70
+Images are numpy uint8 (rows, cols, 4) BGRA arrays or CUDA tensors exposing data_ptr()/stride()
+(device-resident, zero copy); flows are float32 (rows, cols, 2); blend float32 (rows, cols).
+The C++ twin of this file is include/pixflow_b200.hpp.
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _lib
+from ._lib import PixFlowError  # noqa: F401  (re-export)
+
+
+class DirectionHint(enum.IntEnum):
+    """OpticalFlowInterface::DirectionHint, CPU/PixFlow.hpp:19"""
+    UNKNOWN = 0
+    RIGHT = 1
+    DOWN = 2
+    LEFT = 3
+    UP = 4
+
+
+def _is_device_tensor(a):
+    return hasattr(a, "data_ptr") and hasattr(a, "is_cuda")
+
+
+def _view(a, dtype, channels, name):
+    """-> (keepalive, pointer, row_stride_bytes, rows, cols)"""
+    if _is_device_tensor(a):
+        if not a.is_cuda:
+            a = a.numpy()
+        else:
+            exp = {np.uint8: "torch.uint8", np.float32: "torch.float32"}[dtype]
+            if str(a.dtype) != exp:
+                raise TypeError("%s must be %s, got %s" % (name, exp, a.dtype))
+            if a.stride(-1) != 1 or (channels > 1 and (a.dim() != 3 or a.shape[2] != channels or a.stride(1) != channels)):
+                raise ValueError("%s must have densely packed pixels" % name)
+            return a, C.c_void_p(a.data_ptr()), a.stride(0) * a.element_size(), a.shape[0], a.shape[1]
+    a = np.asarray(a)
+    if a.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, np.dtype(dtype), a.dtype))
+    want_ndim = 3 if channels > 1 else 2
+    if a.ndim != want_ndim or (channels > 1 and a.shape[2] != channels):
+        raise ValueError("%s must have shape (rows, cols%s)" % (name, ", %d" % channels if channels > 1 else ""))
+    item = a.itemsize
+    inner_ok = a.strides[-1] == item and (channels == 1 or a.strides[1] == item * channels)
+    if not inner_ok or a.strides[0] < a.shape[1] * item * channels:
+        a = np.ascontiguousarray(a)
+    return a, C.c_void_p(a.ctypes.data), a.strides[0], a.shape[0], a.shape[1]
+
+
+class OpticalFlowInterface:
+    """Abstract boundary, CPU/PixFlow.hpp:15-26"""
+    DirectionHint = DirectionHint
+
+    def computeOpticalFlow(self, I0BGRA, I1BGRA, hint, flow=None):
+        raise NotImplementedError
+
+
+class PixFlow(OpticalFlowInterface):
+    """PixFlow<MaxPercentage> (CPU/PixFlow.hpp:28-457) running on a B200 through libpixflow_b200."""
+
+    def __init__(self, flowAlgName, device=-1):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.flowAlgName = flowAlgName
+        _lib.check(self._lib.pf_engine_create(flowAlgName.encode(), int(device), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pf_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- OpticalFlowInterface::computeOpticalFlow, CPU/PixFlow.hpp:72-135 --
+    def computeOpticalFlow(self, I0BGRA, I1BGRA, hint=DirectionHint.UNKNOWN, flow=None):
+        k0, p0, s0, rows, cols = _view(I0BGRA, np.uint8, 4, "I0BGRA")
+        k1, p1, s1, r1, c1 = _view(I1BGRA, np.uint8, 4, "I1BGRA")
+        if (rows, cols) != (r1, c1):
+            raise ValueError("I0BGRA and I1BGRA must have the same size")
+        if flow is None:
+            flow = np.empty((rows, cols, 2), np.float32)
+        kf, pf_, sf, rf, cf = _view(flow, np.float32, 2, "flow")
+        if (rf, cf) != (rows, cols):
+            raise ValueError("flow must be (rows, cols, 2)")
+        _lib.check(self._lib.pf_compute_flow(self._h, p0, s0, p1, s1, rows, cols, int(hint), pf_, sf))
+        return kf
+
+    # -- NovelViewGeneratorAsymmetricFlow::prepare semantics, CPU/OpticalFlow.cpp:102-145 --
+    def prepareBidirectional(self, imageL, imageR, flowLtoR=None, flowRtoL=None):
+        kl, pl, sl, rows, cols = _view(imageL, np.uint8, 4, "colorImageL")
+        kr, pr, sr, r1, c1 = _view(imageR, np.uint8, 4, "colorImageR")
+        if (rows, cols) != (r1, c1):
+            raise ValueError("colorImageL and colorImageR must have the same size")
+        if flowLtoR is None:
+            flowLtoR = np.empty((rows, cols, 2), np.float32)
+        if flowRtoL is None:
+            flowRtoL = np.empty((rows, cols, 2), np.float32)
+        ka, pa, sa, _, _ = _view(flowLtoR, np.float32, 2, "flowLtoR")
+        kb, pb, sb, _, _ = _view(flowRtoL, np.float32, 2, "flowRtoL")
+        _lib.check(self._lib.pf_prepare_bidirectional(self._h, pl, sl, pr, sr, rows, cols, pa, sa, pb, sb))
+        return ka, kb
+
+    def prepareBidirectionalBatch(self, imagesL, imagesR, flowsLtoR=None, flowsRtoL=None):
+        """n independent pairs of identical size, all in flight concurrently on this engine's device."""
+        n = len(imagesL)
+        vl = [_view(a, np.uint8, 4, "imagesL[%d]" % i) for i, a in enumerate(imagesL)]
+        vr = [_view(a, np.uint8, 4, "imagesR[%d]" % i) for i, a in enumerate(imagesR)]
+        rows, cols = vl[0][3], vl[0][4]
+        if flowsLtoR is None:
+            flowsLtoR = [np.empty((rows, cols, 2), np.float32) for _ in range(n)]
+        if flowsRtoL is None:
+            flowsRtoL = [np.empty((rows, cols, 2), np.float32) for _ in range(n)]
+        va = [_view(a, np.float32, 2, "flowsLtoR[%d]" % i) for i, a in enumerate(flowsLtoR)]
+        vb = [_view(a, np.float32, 2, "flowsRtoL[%d]" % i) for i, a in enumerate(flowsRtoL)]
+        for group in (vl, vr, va, vb):
+            if len(group) != n or any(v[2] != group[0][2] or (v[3], v[4]) != (rows, cols) for v in group):
+                raise ValueError("all pairs of a batch must share size and stride")
+        arr = lambda vs: (C.c_void_p * n)(*[v[1].value for v in vs])
+        _lib.check(self._lib.pf_prepare_bidirectional_batch(
+            self._h, n, arr(vl), vl[0][2], arr(vr), vr[0][2], rows, cols, arr(va), va[0][2], arr(vb), vb[0][2]))
+        return [v[0] for v in va], [v[0] for v in vb]
+
+    def combineNovelViews(self, imageL, imageR, flowLtoR, flowRtoL, blend, out=None):
+        kl, pl, sl, rows, cols = _view(imageL, np.uint8, 4, "imageL")
+        kr, pr, sr, _, _ = _view(imageR, np.uint8, 4, "imageR")
+        ka, pa, sa, _, _ = _view(flowLtoR, np.float32, 2, "flowLtoR")
+        kb, pb, sb, _, _ = _view(flowRtoL, np.float32, 2, "flowRtoL")
+        kc, pc, sc, _, _ = _view(blend, np.float32, 1, "blend")
+        if out is None:
+            out = np.empty((rows, cols, 4), np.uint8)
+        ko, po, so, _, _ = _view(out, np.uint8, 4, "out")
+        _lib.check(self._lib.pf_combine_novel_views(self._h, pl, sl, pr, sr, pa, sa, pb, sb, pc, sc, rows, cols, po, so))
+        return ko
+
+    def novelView(self, imageL, imageR, blend, out=None, flowLtoR=None, flowRtoL=None):
+        """prepare + setBlend + generateNovelView fused on the device (CPU/main.cpp:82-89)."""
+        kl, pl, sl, rows, cols = _view(imageL, np.uint8, 4, "imageL")
+        kr, pr, sr, _, _ = _view(imageR, np.uint8, 4, "imageR")
+        kc, pc, sc, _, _ = _view(blend, np.float32, 1, "blend")
+        if out is None:
+            out = np.empty((rows, cols, 4), np.uint8)
+        ko, po, so, _, _ = _view(out, np.uint8, 4, "out")
+        pa = pb = C.c_void_p()
+        sa = sb = 0
+        if flowLtoR is not None:
+            ka, pa, sa, _, _ = _view(flowLtoR, np.float32, 2, "flowLtoR")
+        if flowRtoL is not None:
+            kb, pb, sb, _, _ = _view(flowRtoL, np.float32, 2, "flowRtoL")
+        _lib.check(self._lib.pf_novel_view(self._h, pl, sl, pr, sr, pc, sc, rows, cols, po, so, pa, sa, pb, sb))
+        return ko
+
+    # -- instrumentation used by bench.py --
+    def setSweepTiming(self, enabled):
+        _lib.check(self._lib.pf_set_sweep_timing(self._h, int(bool(enabled))))
+
+    def lastSweepMs(self):
+        return float(self._lib.pf_last_sweep_ms(self._h)), int(self._lib.pf_last_sweep_launches(self._h))
+
+
+def makeOpticalFlowByName(flowAlgName, device=-1):
+    """CPU/PixFlow.hpp:459-500: "pixflow_low" -> PixFlow<0>, "pixflow_search_20" -> PixFlow<20>;
+    anything else raises (reference: throw VrCamException("unrecognized flow algorithm name: ..."))."""
+    return PixFlow(flowAlgName, device)
+
+
+class NovelViewUtil:
+    """CPU/OpticalFlow.hpp:19-32"""
+
+    @staticmethod
+    def combineNovelViews(imageL, imageR, flowLtoR, flowRtoL, blend, flowAlg=None):
+        own = flowAlg is None
+        alg = makeOpticalFlowByName("pixflow_low") if own else flowAlg
+        try:
+            return alg.combineNovelViews(imageL, imageR, flowLtoR, flowRtoL, blend)
+        finally:
+            if own:
+                alg.close()
+
+
+class NovelViewGenerator:
+    """CPU/OpticalFlow.hpp:34-48"""
+
+    def prepare(self, colorImageL, colorImageR):
+        raise NotImplementedError
+
+    def generateNovelView(self):
+        raise NotImplementedError
+
+    def getFlowLtoR(self):
+        return None
+
+    def getFlowRtoL(self):
+        return None
+
+    def setBlend(self, blend):
+        raise NotImplementedError
+
+
+class NovelViewGeneratorAsymmetricFlow(NovelViewGenerator):
+    """CPU/OpticalFlow.hpp:50-70, CPU/OpticalFlow.cpp:94-145"""
+
+    def __init__(self, flowAlgName, device=-1):
+        self.flowAlgName = flowAlgName
+        self._alg = makeOpticalFlowByName(flowAlgName, device)   # raises on an unknown name, like prepare() would
+        self.imageL = self.imageR = None
+        self.flowLtoR = self.flowRtoL = None
+        self.Blend = None
+
+    def prepare(self, colorImageL, colorImageR):
+        self.imageL = np.array(colorImageL, copy=True)   # .clone(), CPU/OpticalFlow.cpp:106-107
+        self.imageR = np.array(colorImageR, copy=True)
+        self.flowLtoR, self.flowRtoL = self._alg.prepareBidirectional(self.imageL, self.imageR)
+
+    def setBlend(self, blend):
+        self.Blend = np.array(blend, dtype=np.float32, copy=True)   # blend.clone(), CPU/OpticalFlow.hpp:69
+
+    def generateNovelView(self):
+        return self._alg.combineNovelViews(self.imageL, self.imageR, self.flowLtoR, self.flowRtoL, self.Blend)
+
+    def getFlowLtoR(self):
+        return self.flowLtoR
+
+    def getFlowRtoL(self):
+        return self.flowRtoL
+
+    def close(self):
+        self._alg.close()

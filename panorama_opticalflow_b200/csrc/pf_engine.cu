@@ -1,0 +1,679 @@
+// pf_engine.cu -- host-side engine and the C-ABI of libpixflow_b200.so (include/pixflow_b200.h).
+//
+// The engine owns per-pair workspaces in HBM (pyramids, gradients, per-direction flow buffers, boundary
+// arenas), three streams per workspace (shared front end + one per flow direction) and enqueues the whole
+// coarse-to-fine loop without any host round trip; the two directions L->R and R->L share the front end,
+// pyramids and gradients (the reference recomputes them per direction, CPU/OpticalFlow.cpp:130-139).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pixflow_b200.h"
+#include "pf_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define PF_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(PF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// ---- geometry of one flow problem (CPU/PixFlow.hpp:80-81, :137-151) -----------------------------------
+struct Plan {
+    int rows = 0, cols = 0, pad = 0, pcols = 0;
+    int dh = 0, dw = 0, L = 0;
+    std::vector<int> ws, hs;
+    std::vector<size_t> off;       // pixel offset of each level in the pyramid arrays
+    size_t total_px = 0;
+    std::vector<size_t> bnd_off;   // per (level, sweep) offset in uint4 lines
+    size_t bnd_lines = 0;
+
+    void build(int rows_, int cols_, int pad_) {
+        rows = rows_; cols = cols_; pad = pad_; pcols = cols + 2 * pad;
+        dw = (int)((float)pcols * 0.5f);
+        dh = (int)((float)rows * 0.5f);
+        ws.clear(); hs.clear(); off.clear(); bnd_off.clear();
+        ws.push_back(dw); hs.push_back(dh);
+        while (ws.size() < 1000) {
+            const int nw = (int)((float)ws.back() * 0.9f + 0.5f);
+            const int nh = (int)((float)hs.back() * 0.9f + 0.5f);
+            if (nh <= 24 || nw <= 24) break;
+            ws.push_back(nw); hs.push_back(nh);
+        }
+        L = (int)ws.size();
+        total_px = 0;
+        bnd_lines = 0;
+        for (int l = 0; l < L; ++l) {
+            off.push_back(total_px);
+            total_px += ((size_t)ws[l] * hs[l] + 63) & ~(size_t)63;   // keep every level 256-byte aligned
+            for (int s = 0; s < 2; ++s) {
+                bnd_off.push_back(bnd_lines);
+                bnd_lines += pf::sweep_boundary_lines(hs[l], ws[l]);
+            }
+        }
+    }
+};
+
+struct Workspace {
+    Plan plan;
+    int ndir = 2;
+    uint8_t* in[2] = {nullptr, nullptr};          // staged BGRA inputs (rows x cols x 4, dense)
+    float* I[2] = {nullptr, nullptr};
+    float* A[2] = {nullptr, nullptr};
+    float* Ipre = nullptr;
+    float2* G[2] = {nullptr, nullptr};
+    float2* bufA[2] = {nullptr, nullptr};         // per direction: flow ping
+    float2* bufB[2] = {nullptr, nullptr};         // flow pong
+    float2* bufT[2] = {nullptr, nullptr};         // blur row-pass temp
+    float2* blurred[2] = {nullptr, nullptr};
+    float* ratio[2] = {nullptr, nullptr};
+    uint4* bnd[2] = {nullptr, nullptr};
+    int* tickets[2] = {nullptr, nullptr};
+    float2* out[2] = {nullptr, nullptr};          // rows x cols flows (dense)
+    uint8_t* merged = nullptr;                    // rows x cols BGRA (novel view)
+    float* blend = nullptr;
+    cudaStream_t sMain = nullptr, sDir[2] = {nullptr, nullptr};
+    cudaEvent_t evReady = nullptr, evDone[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> sweepEv[2];          // optional timing events
+    size_t nSweepEv[2] = {0, 0};
+
+    ~Workspace() { release(); }
+    void release() {
+        for (int k = 0; k < 2; ++k) {
+            cudaFree(in[k]); cudaFree(I[k]); cudaFree(A[k]); cudaFree(G[k]);
+            cudaFree(bufA[k]); cudaFree(bufB[k]); cudaFree(bufT[k]); cudaFree(blurred[k]);
+            cudaFree(ratio[k]); cudaFree(bnd[k]); cudaFree(tickets[k]); cudaFree(out[k]);
+            in[k] = nullptr; I[k] = A[k] = nullptr; G[k] = nullptr; bufA[k] = bufB[k] = bufT[k] = blurred[k] = nullptr;
+            ratio[k] = nullptr; bnd[k] = nullptr; tickets[k] = nullptr; out[k] = nullptr;
+            if (sDir[k]) cudaStreamDestroy(sDir[k]);
+            if (evDone[k]) cudaEventDestroy(evDone[k]);
+            sDir[k] = nullptr; evDone[k] = nullptr;
+            for (auto e : sweepEv[k]) cudaEventDestroy(e);
+            sweepEv[k].clear();
+        }
+        cudaFree(Ipre); cudaFree(merged); cudaFree(blend);
+        Ipre = nullptr; merged = nullptr; blend = nullptr;
+        if (sMain) cudaStreamDestroy(sMain);
+        if (evReady) cudaEventDestroy(evReady);
+        sMain = nullptr; evReady = nullptr;
+    }
+
+    int init(int rows, int cols, int pad) {
+        plan.build(rows, cols, pad);
+        const Plan& p = plan;
+        const size_t px0 = (size_t)p.dw * p.dh;
+        for (int k = 0; k < 2; ++k) {
+            PF_CUDA(cudaMalloc(&in[k], (size_t)rows * cols * 4));
+            PF_CUDA(cudaMalloc(&I[k], p.total_px * sizeof(float)));
+            PF_CUDA(cudaMalloc(&A[k], p.total_px * sizeof(float)));
+            PF_CUDA(cudaMalloc(&G[k], p.total_px * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&bufA[k], px0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&bufB[k], px0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&bufT[k], px0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&blurred[k], px0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&ratio[k], 256));
+            PF_CUDA(cudaMalloc(&bnd[k], (p.bnd_lines + 1) * sizeof(uint4)));
+            PF_CUDA(cudaMalloc(&tickets[k], (size_t)p.L * 2 * sizeof(int)));
+            PF_CUDA(cudaMalloc(&out[k], (size_t)rows * cols * sizeof(float2)));
+            PF_CUDA(cudaStreamCreateWithFlags(&sDir[k], cudaStreamNonBlocking));
+            PF_CUDA(cudaEventCreateWithFlags(&evDone[k], cudaEventDisableTiming));
+        }
+        PF_CUDA(cudaMalloc(&Ipre, px0 * sizeof(float)));
+        PF_CUDA(cudaStreamCreateWithFlags(&sMain, cudaStreamNonBlocking));
+        PF_CUDA(cudaEventCreateWithFlags(&evReady, cudaEventDisableTiming));
+        return PF_OK;
+    }
+};
+
+}  // namespace
+
+struct pf_engine {
+    int device = 0;
+    int max_percentage = 0;     // template parameter of PixFlow<MaxPercentage>
+    int search_dist = 0;        // computeSearchDistance, CPU/PixFlow.hpp:153-155
+    bool time_sweeps = false;
+    double last_sweep_ms = 0.0;
+    uint64_t last_sweep_launches = 0;
+    std::mutex mu;
+    std::vector<Workspace*> pool;
+
+    ~pf_engine() { for (auto* w : pool) delete w; }
+
+    // workspace #idx for the given geometry (created or re-created on demand)
+    int workspace(int idx, int rows, int cols, int pad, Workspace** out) {
+        while ((int)pool.size() <= idx) pool.push_back(nullptr);
+        Workspace* w = pool[idx];
+        if (w && (w->plan.rows != rows || w->plan.cols != cols || w->plan.pad != pad)) { delete w; w = nullptr; }
+        if (!w) {
+            w = new Workspace();
+            const int rc = w->init(rows, cols, pad);
+            if (rc != PF_OK) { delete w; pool[idx] = nullptr; return rc; }
+            pool[idx] = w;
+        }
+        *out = w;
+        return PF_OK;
+    }
+};
+
+namespace {
+
+#define LAUNCHED(n) g_launches.fetch_add((n), std::memory_order_relaxed)
+
+cudaEvent_t next_sweep_event(Workspace& w, int d) {
+    if (w.nSweepEv[d] == w.sweepEv[d].size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        w.sweepEv[d].push_back(e);
+    }
+    return w.sweepEv[d][w.nSweepEv[d]++];
+}
+
+// front end + pyramids + gradients for both images, on sMain (CPU/PixFlow.hpp:78-110, :284-294)
+int enqueue_shared(pf_engine* e, Workspace& w, const uint8_t* img[2], const size_t stride[2]) {
+    const Plan& p = w.plan;
+    (void)e;
+    for (int k = 0; k < 2; ++k) {
+        pf::launch_frontend_resize(img[k], stride[k], p.rows, p.cols, p.pad, w.Ipre, w.A[k] + p.off[0], p.dh, p.dw, w.sMain);
+        pf::launch_gauss5(w.Ipre, w.I[k] + p.off[0], p.dh, p.dw, w.sMain);
+        LAUNCHED(2);
+    }
+    for (int l = 1; l < p.L; ++l) {
+        pf::PlaneSet ps;
+        for (int k = 0; k < 2; ++k) {
+            ps.src[k] = w.I[k] + p.off[l - 1]; ps.dst[k] = w.I[k] + p.off[l];
+            ps.src[2 + k] = w.A[k] + p.off[l - 1]; ps.dst[2 + k] = w.A[k] + p.off[l];
+        }
+        pf::launch_pyr_down(ps, 4, p.hs[l - 1], p.ws[l - 1], p.hs[l], p.ws[l], w.sMain);
+        LAUNCHED(1);
+    }
+    for (int l = 0; l < p.L; ++l)
+        for (int k = 0; k < 2; ++k) {
+            pf::launch_gradient(w.I[k] + p.off[l], w.G[k] + p.off[l], p.hs[l], p.ws[l], w.sMain);
+            LAUNCHED(1);
+        }
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaEventRecord(w.evReady, w.sMain));
+    return PF_OK;
+}
+
+// coarse-to-fine loop of one direction on sDir[d] (CPU/PixFlow.hpp:112-134); i0 = index of image I0
+int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float2* out, size_t out_stride) {
+    const Plan& p = w.plan;
+    const int i1 = 1 - i0;
+    cudaStream_t st = w.sDir[d];
+    PF_CUDA(cudaStreamWaitEvent(st, w.evReady, 0));
+    PF_CUDA(cudaMemsetAsync(w.bnd[d], 0, (p.bnd_lines + 1) * sizeof(uint4), st));
+    PF_CUDA(cudaMemsetAsync(w.tickets[d], 0, (size_t)p.L * 2 * sizeof(int), st));
+    float2* flow = w.bufA[d];
+    float2* other = w.bufB[d];
+    for (int l = p.L - 1; l >= 0; --l) {
+        const int h = p.hs[l], wd = p.ws[l];
+        const float* I0 = w.I[i0] + p.off[l];
+        const float* I1 = w.I[i1] + p.off[l];
+        const float* A0 = w.A[i0] + p.off[l];
+        const float* A1 = w.A[i1] + p.off[l];
+        if (l == p.L - 1) {
+            pf::launch_initial_flow(I0, I1, A0, A1, flow, w.ratio[d], h, wd, hint, e->search_dist, st);
+            LAUNCHED(e->search_dist > 0 && hint != PF_HINT_UNKNOWN ? 2 : 1);
+        }
+        pf::launch_blur15_rows(flow, w.bufT[d], h, wd, st);
+        pf::launch_blur15_cols(w.bufT[d], w.blurred[d], h, wd, nullptr, nullptr, nullptr, st);
+        pf::SweepArgs sa;
+        sa.alpha0 = A0; sa.alpha1 = A1;
+        sa.G0 = w.G[i0] + p.off[l]; sa.G1 = w.G[i1] + p.off[l];
+        sa.blurred = w.blurred[d];
+        sa.h = h; sa.w = wd;
+        // forward sweep, in place on `flow`
+        sa.flow = flow;
+        sa.boundary = w.bnd[d] + p.bnd_off[2 * l];
+        sa.ticket = w.tickets[d] + 2 * l;
+        if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
+        pf::launch_sweep(sa, +1, st);
+        if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
+        pf::launch_median5(flow, other, h, wd, st);
+        // backward sweep, in place on `other`
+        sa.flow = other;
+        sa.boundary = w.bnd[d] + p.bnd_off[2 * l + 1];
+        sa.ticket = w.tickets[d] + 2 * l + 1;
+        if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
+        pf::launch_sweep(sa, -1, st);
+        if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
+        pf::launch_median5(other, flow, h, wd, st);
+        // lowAlphaFlowDiffusion: blur + blend, written to `other`
+        pf::launch_blur15_rows(flow, w.bufT[d], h, wd, st);
+        pf::launch_blur15_cols(w.bufT[d], other, h, wd, A0, A1, flow, st);
+        LAUNCHED(8);
+        if (l > 0) {
+            pf::launch_upsample_cubic(other, h, wd, flow, p.hs[l - 1], p.ws[l - 1], st);
+            LAUNCHED(1);
+        } else {
+            pf::launch_tail(other, h, wd, p.rows, p.pcols, p.pad, p.cols, out, out_stride, st);
+            LAUNCHED(1);
+        }
+    }
+    PF_CUDA(cudaGetLastError());
+    return PF_OK;
+}
+
+int collect_sweep_timing(pf_engine* e, std::vector<Workspace*>& used) {
+    e->last_sweep_ms = 0.0;
+    e->last_sweep_launches = 0;
+    if (!e->time_sweeps) return PF_OK;
+    for (Workspace* w : used)
+        for (int d = 0; d < 2; ++d) {
+            for (size_t i = 0; i + 1 < w->nSweepEv[d]; i += 2) {
+                float ms = 0.0f;
+                PF_CUDA(cudaEventElapsedTime(&ms, w->sweepEv[d][i], w->sweepEv[d][i + 1]));
+                e->last_sweep_ms += ms;
+                e->last_sweep_launches += 1;
+            }
+            w->nSweepEv[d] = 0;
+        }
+    return PF_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_image_args(const void* p, size_t stride, int rows, int cols, size_t elem, const char* what) {
+    if (!p) return fail(PF_ERR_INVALID_ARGUMENT, "%s is NULL", what);
+    if (rows <= 0 || cols <= 0) return fail(PF_ERR_INVALID_ARGUMENT, "rows/cols must be positive");
+    if (stride < (size_t)cols * elem) return fail(PF_ERR_INVALID_ARGUMENT, "%s stride %zu < cols*%zu", what, stride, elem);
+    if (stride % 4 != 0 || ((uintptr_t)p) % 4 != 0) return fail(PF_ERR_INVALID_ARGUMENT, "%s must be 4-byte aligned", what);
+    return PF_OK;
+}
+
+// stage an input image: device pointers are used in place, host pointers are copied into ws.in[k]
+int stage_input(Workspace& w, int k, const void* img, size_t stride, const uint8_t** dptr, size_t* dstride, cudaStream_t st) {
+    if (is_device_ptr(img)) { *dptr = (const uint8_t*)img; *dstride = stride; return PF_OK; }
+    const size_t dense = (size_t)w.plan.cols * 4;
+    PF_CUDA(cudaMemcpy2DAsync(w.in[k], dense, img, stride, dense, w.plan.rows, cudaMemcpyHostToDevice, st));
+    *dptr = w.in[k]; *dstride = dense;
+    return PF_OK;
+}
+
+// the body shared by compute_flow / prepare / batch / novel_view for ONE pair on workspace w (asynchronous)
+int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, const void* imgR, size_t strideR,
+                 int ndir, const int hints[2], void* outs[2], const size_t ostrides[2],
+                 const uint8_t* dimg[2], size_t dstride[2], float2* dflow[2], size_t dfstride[2]) {
+    int rc;
+    if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], w.sMain)) != PF_OK) return rc;
+    if ((rc = stage_input(w, 1, imgR, strideR, &dimg[1], &dstride[1], w.sMain)) != PF_OK) return rc;
+    if ((rc = enqueue_shared(e, w, dimg, dstride)) != PF_OK) return rc;
+    for (int d = 0; d < ndir; ++d) {
+        const bool dev_out = outs[d] && is_device_ptr(outs[d]);
+        dflow[d] = dev_out ? (float2*)outs[d] : w.out[d];
+        dfstride[d] = dev_out ? ostrides[d] : (size_t)w.plan.cols * sizeof(float2);
+        if ((rc = enqueue_direction(e, w, d, d == 0 ? 0 : 1, hints[d], dflow[d], dfstride[d])) != PF_OK) return rc;
+        if (outs[d] && !dev_out)
+            PF_CUDA(cudaMemcpy2DAsync(outs[d], ostrides[d], w.out[d], dfstride[d], (size_t)w.plan.cols * sizeof(float2),
+                                      w.plan.rows, cudaMemcpyDeviceToHost, w.sDir[d]));
+        PF_CUDA(cudaEventRecord(w.evDone[d], w.sDir[d]));
+    }
+    return PF_OK;
+}
+
+int sync_pair(Workspace& w, int ndir) {
+    for (int d = 0; d < ndir; ++d) PF_CUDA(cudaStreamSynchronize(w.sDir[d]));
+    PF_CUDA(cudaStreamSynchronize(w.sMain));
+    return PF_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// C-ABI
+// ======================================================================================================
+extern "C" {
+
+const char* pf_last_error(void) { return g_err.c_str(); }
+const char* pf_version(void) { return "pixflow_b200 0.1 (sm_100a)"; }
+uint64_t pf_kernel_launch_count(void) { return g_launches.load(); }
+
+int pf_engine_create(const char* name, int device, pf_engine** out) {
+    if (!out) return fail(PF_ERR_INVALID_ARGUMENT, "out_engine is NULL");
+    *out = nullptr;
+    if (!name) return fail(PF_ERR_INVALID_ARGUMENT, "flow_alg_name is NULL");
+    int pct;
+    if (strcmp(name, "pixflow_low") == 0) pct = 0;
+    else if (strcmp(name, "pixflow_search_20") == 0) pct = 20;
+    else return fail(PF_ERR_UNKNOWN_ALGORITHM, "unrecognized flow algorithm name: %s", name);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PF_ERR_NO_DEVICE, "no CUDA device available: libpixflow_b200 has no CPU fallback");
+    }
+    if (device < 0) PF_CUDA(cudaGetDevice(&device));
+    if (device >= ndev) return fail(PF_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(PF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    pf_engine* e = new pf_engine();
+    e->device = device;
+    e->max_percentage = pct;
+    e->search_dist = (24 * pct + 50) / 100;
+    *out = e;
+    g_err.clear();
+    return PF_OK;
+}
+
+void pf_engine_destroy(pf_engine* e) {
+    if (!e) return;
+    {
+        DeviceGuard g(e->device);
+        cudaDeviceSynchronize();
+        delete e;
+    }
+}
+
+int pf_set_sweep_timing(pf_engine* e, int enabled) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    e->time_sweeps = enabled != 0;
+    return PF_OK;
+}
+double pf_last_sweep_ms(pf_engine* e) { return e ? e->last_sweep_ms : 0.0; }
+uint64_t pf_last_sweep_launches(pf_engine* e) { return e ? e->last_sweep_launches : 0; }
+
+int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, size_t s1, int rows, int cols, int hint,
+                    void* flow_out, size_t flow_stride) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    int rc;
+    if ((rc = check_image_args(i0, s0, rows, cols, 4, "I0BGRA")) != PF_OK) return rc;
+    if ((rc = check_image_args(i1, s1, rows, cols, 4, "I1BGRA")) != PF_OK) return rc;
+    if ((rc = check_image_args(flow_out, flow_stride, rows, cols, 8, "flow")) != PF_OK) return rc;
+    if (hint < 0 || hint > 4) return fail(PF_ERR_INVALID_ARGUMENT, "unexpected direction %d", hint);
+    if ((int)((float)cols * 0.5f) < 4 || (int)((float)rows * 0.5f) < 4) return fail(PF_ERR_INVALID_ARGUMENT, "image too small");
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    Workspace* w;
+    if ((rc = e->workspace(0, rows, cols, 0, &w)) != PF_OK) return rc;
+    const int hints[2] = {hint, 0};
+    void* outs[2] = {flow_out, nullptr};
+    const size_t ostr[2] = {flow_stride, 0};
+    const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
+    if ((rc = enqueue_pair(e, *w, i0, s0, i1, s1, 1, hints, outs, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
+    if ((rc = sync_pair(*w, 1)) != PF_OK) return rc;
+    std::vector<Workspace*> used{w};
+    return collect_sweep_timing(e, used);
+}
+
+int pf_prepare_bidirectional_batch(pf_engine* e, int n, const void* const* Ls, size_t sl, const void* const* Rs, size_t sr,
+                                   int rows, int cols, void* const* lr, size_t slr, void* const* rl, size_t srl) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    if (n <= 0 || !Ls || !Rs || !lr || !rl) return fail(PF_ERR_INVALID_ARGUMENT, "bad batch arguments");
+    int rc;
+    for (int i = 0; i < n; ++i) {
+        if ((rc = check_image_args(Ls[i], sl, rows, cols, 4, "imageL")) != PF_OK) return rc;
+        if ((rc = check_image_args(Rs[i], sr, rows, cols, 4, "imageR")) != PF_OK) return rc;
+        if ((rc = check_image_args(lr[i], slr, rows, cols, 8, "flowLtoR")) != PF_OK) return rc;
+        if ((rc = check_image_args(rl[i], srl, rows, cols, 8, "flowRtoL")) != PF_OK) return rc;
+    }
+    const int pad = cols / 20;   // CPU/OpticalFlow.cpp:113
+    if ((int)((float)(cols + 2 * pad) * 0.5f) < 4 || (int)((float)rows * 0.5f) < 4) return fail(PF_ERR_INVALID_ARGUMENT, "image too small");
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    std::vector<Workspace*> used;
+    const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};   // CPU/OpticalFlow.cpp:130-139
+    for (int i = 0; i < n; ++i) {
+        Workspace* w;
+        if ((rc = e->workspace(i, rows, cols, pad, &w)) != PF_OK) return rc;
+        used.push_back(w);
+        void* outs[2] = {lr[i], rl[i]};
+        const size_t ostr[2] = {slr, srl};
+        const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
+        if ((rc = enqueue_pair(e, *w, Ls[i], sl, Rs[i], sr, 2, hints, outs, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
+    }
+    for (Workspace* w : used)
+        if ((rc = sync_pair(*w, 2)) != PF_OK) return rc;
+    return collect_sweep_timing(e, used);
+}
+
+int pf_prepare_bidirectional(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, int rows, int cols,
+                             void* lr, size_t slr, void* rl, size_t srl) {
+    const void* Ls[1] = {L};
+    const void* Rs[1] = {R};
+    void* lrs[1] = {lr};
+    void* rls[1] = {rl};
+    return pf_prepare_bidirectional_batch(e, 1, Ls, sl, Rs, sr, rows, cols, lrs, slr, rls, srl);
+}
+
+static int combine_impl(pf_engine* e, Workspace* w, cudaStream_t st, const uint8_t* dL, size_t sL, const uint8_t* dR, size_t sR,
+                        const float2* dLR, size_t sLR, const float2* dRL, size_t sRL, const void* blend, size_t sB,
+                        int rows, int cols, void* out, size_t sOut) {
+    (void)e;
+    const float* dB;
+    size_t dsB;
+    if (is_device_ptr(blend)) { dB = (const float*)blend; dsB = sB; }
+    else {
+        if (!w->blend) PF_CUDA(cudaMalloc(&w->blend, (size_t)rows * cols * 4));
+        PF_CUDA(cudaMemcpy2DAsync(w->blend, (size_t)cols * 4, blend, sB, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, st));
+        dB = w->blend; dsB = (size_t)cols * 4;
+    }
+    const bool dev_out = is_device_ptr(out);
+    uint8_t* dO;
+    size_t dsO;
+    if (dev_out) { dO = (uint8_t*)out; dsO = sOut; }
+    else {
+        if (!w->merged) PF_CUDA(cudaMalloc(&w->merged, (size_t)rows * cols * 4));
+        dO = w->merged; dsO = (size_t)cols * 4;
+    }
+    pf::launch_combine(dL, sL, dR, sR, dLR, sLR, dRL, sRL, dB, dsB, rows, cols, dO, dsO, st);
+    LAUNCHED(1);
+    PF_CUDA(cudaGetLastError());
+    if (!dev_out) PF_CUDA(cudaMemcpy2DAsync(out, sOut, dO, dsO, (size_t)cols * 4, rows, cudaMemcpyDeviceToHost, st));
+    return PF_OK;
+}
+
+int pf_combine_novel_views(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, const void* lr, size_t slr,
+                           const void* rl, size_t srl, const void* blend, size_t sb, int rows, int cols, void* out, size_t so) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    int rc;
+    if ((rc = check_image_args(L, sl, rows, cols, 4, "imageL")) != PF_OK) return rc;
+    if ((rc = check_image_args(R, sr, rows, cols, 4, "imageR")) != PF_OK) return rc;
+    if ((rc = check_image_args(lr, slr, rows, cols, 8, "flowLtoR")) != PF_OK) return rc;
+    if ((rc = check_image_args(rl, srl, rows, cols, 8, "flowRtoL")) != PF_OK) return rc;
+    if ((rc = check_image_args(blend, sb, rows, cols, 4, "blend")) != PF_OK) return rc;
+    if ((rc = check_image_args(out, so, rows, cols, 4, "out")) != PF_OK) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    Workspace* w;
+    if ((rc = e->workspace(0, rows, cols, cols / 20, &w)) != PF_OK) return rc;
+    cudaStream_t st = w->sMain;
+    const uint8_t* dimg[2]; size_t dstr[2];
+    if ((rc = stage_input(*w, 0, L, sl, &dimg[0], &dstr[0], st)) != PF_OK) return rc;
+    if ((rc = stage_input(*w, 1, R, sr, &dimg[1], &dstr[1], st)) != PF_OK) return rc;
+    const float2* dfl[2]; size_t dfs[2];
+    const void* fl[2] = {lr, rl};
+    const size_t fs[2] = {slr, srl};
+    for (int d = 0; d < 2; ++d) {
+        if (is_device_ptr(fl[d])) { dfl[d] = (const float2*)fl[d]; dfs[d] = fs[d]; }
+        else {
+            PF_CUDA(cudaMemcpy2DAsync(w->out[d], (size_t)cols * 8, fl[d], fs[d], (size_t)cols * 8, rows, cudaMemcpyHostToDevice, st));
+            dfl[d] = w->out[d]; dfs[d] = (size_t)cols * 8;
+        }
+    }
+    if ((rc = combine_impl(e, w, st, dimg[0], dstr[0], dimg[1], dstr[1], dfl[0], dfs[0], dfl[1], dfs[1], blend, sb, rows, cols, out, so)) != PF_OK) return rc;
+    PF_CUDA(cudaStreamSynchronize(st));
+    return PF_OK;
+}
+
+int pf_novel_view(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, const void* blend, size_t sb,
+                  int rows, int cols, void* out, size_t so, void* lr, size_t slr, void* rl, size_t srl) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    int rc;
+    if ((rc = check_image_args(L, sl, rows, cols, 4, "imageL")) != PF_OK) return rc;
+    if ((rc = check_image_args(R, sr, rows, cols, 4, "imageR")) != PF_OK) return rc;
+    if ((rc = check_image_args(blend, sb, rows, cols, 4, "blend")) != PF_OK) return rc;
+    if ((rc = check_image_args(out, so, rows, cols, 4, "out")) != PF_OK) return rc;
+    if (lr && (rc = check_image_args(lr, slr, rows, cols, 8, "flowLtoR")) != PF_OK) return rc;
+    if (rl && (rc = check_image_args(rl, srl, rows, cols, 8, "flowRtoL")) != PF_OK) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    Workspace* w;
+    const int pad = cols / 20;
+    if ((rc = e->workspace(0, rows, cols, pad, &w)) != PF_OK) return rc;
+    const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};
+    void* outs[2] = {lr, rl};
+    const size_t ostr[2] = {slr, srl};
+    const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
+    if ((rc = enqueue_pair(e, *w, L, sl, R, sr, 2, hints, outs, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
+    // join both directions into sMain, then blend there
+    for (int d = 0; d < 2; ++d) PF_CUDA(cudaStreamWaitEvent(w->sMain, w->evDone[d], 0));
+    if ((rc = combine_impl(e, w, w->sMain, dimg[0], dstr[0], dimg[1], dstr[1], dflow[0], dfs[0], dflow[1], dfs[1],
+                           blend, sb, rows, cols, out, so)) != PF_OK) return rc;
+    if ((rc = sync_pair(*w, 2)) != PF_OK) return rc;
+    std::vector<Workspace*> used{w};
+    return collect_sweep_timing(e, used);
+}
+
+int pf_host_alloc(void** p, size_t bytes) {
+    if (!p) return fail(PF_ERR_INVALID_ARGUMENT, "ptr is NULL");
+    PF_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return PF_OK;
+}
+int pf_host_free(void* p) {
+    PF_CUDA(cudaFreeHost(p));
+    return PF_OK;
+}
+
+}  // extern "C"
+
+// ---- diagnostic single-stage entry points ---------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t n) { PF_CUDA(cudaMalloc(&p, n ? n : 1)); return PF_OK; }
+    int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; PF_CUDA(cudaMemcpy(p, h, n, cudaMemcpyHostToDevice)); return PF_OK; }
+    int download(void* h, size_t n) { PF_CUDA(cudaDeviceSynchronize()); PF_CUDA(cudaGetLastError()); PF_CUDA(cudaMemcpy(h, p, n, cudaMemcpyDeviceToHost)); return PF_OK; }
+    template <class T> T* as() { return (T*)p; }
+};
+#define RC(x) do { int rc_ = (x); if (rc_ != PF_OK) return rc_; } while (0)
+}  // namespace
+
+extern "C" {
+
+int pf_stage_frontend(const void* bgra, int rows, int cols, int pad, float* grey, float* alpha, int dh, int dw) {
+    DevBuf in, g, a;
+    const size_t n = (size_t)dh * dw * 4;
+    RC(in.upload(bgra, (size_t)rows * cols * 4)); RC(g.alloc(n)); RC(a.alloc(n));
+    pf::launch_frontend_resize(in.as<uint8_t>(), (size_t)cols * 4, rows, cols, pad, g.as<float>(), a.as<float>(), dh, dw, 0);
+    LAUNCHED(1);
+    RC(g.download(grey, n));
+    return a.download(alpha, n);
+}
+int pf_stage_gauss5(const float* src, float* dst, int h, int w) {
+    DevBuf s, d;
+    const size_t n = (size_t)h * w * 4;
+    RC(s.upload(src, n)); RC(d.alloc(n));
+    pf::launch_gauss5(s.as<float>(), d.as<float>(), h, w, 0);
+    LAUNCHED(1);
+    return d.download(dst, n);
+}
+int pf_stage_pyr_down(const float* src, int sh, int sw, float* dst, int dh, int dw) {
+    DevBuf s, d;
+    RC(s.upload(src, (size_t)sh * sw * 4)); RC(d.alloc((size_t)dh * dw * 4));
+    pf::PlaneSet ps{};
+    ps.src[0] = s.as<float>(); ps.dst[0] = d.as<float>();
+    pf::launch_pyr_down(ps, 1, sh, sw, dh, dw, 0);
+    LAUNCHED(1);
+    return d.download(dst, (size_t)dh * dw * 4);
+}
+int pf_stage_gradient(const float* I, float* G, int h, int w) {
+    DevBuf s, d;
+    RC(s.upload(I, (size_t)h * w * 4)); RC(d.alloc((size_t)h * w * 8));
+    pf::launch_gradient(s.as<float>(), d.as<float2>(), h, w, 0);
+    LAUNCHED(1);
+    return d.download(G, (size_t)h * w * 8);
+}
+int pf_stage_blur15(const float* flow, float* dst, int h, int w, const float* alpha0, const float* alpha1) {
+    DevBuf s, t, d, a0, a1;
+    const size_t n = (size_t)h * w * 8;
+    RC(s.upload(flow, n)); RC(t.alloc(n)); RC(d.alloc(n));
+    if (alpha0) { RC(a0.upload(alpha0, n / 2)); RC(a1.upload(alpha1, n / 2)); }
+    pf::launch_blur15_rows(s.as<float2>(), t.as<float2>(), h, w, 0);
+    pf::launch_blur15_cols(t.as<float2>(), d.as<float2>(), h, w, alpha0 ? a0.as<float>() : nullptr, alpha0 ? a1.as<float>() : nullptr,
+                           s.as<float2>(), 0);
+    LAUNCHED(2);
+    return d.download(dst, n);
+}
+int pf_stage_median5(const float* flow, float* dst, int h, int w) {
+    DevBuf s, d;
+    const size_t n = (size_t)h * w * 8;
+    RC(s.upload(flow, n)); RC(d.alloc(n));
+    pf::launch_median5(s.as<float2>(), d.as<float2>(), h, w, 0);
+    LAUNCHED(1);
+    return d.download(dst, n);
+}
+int pf_stage_sweep(const float* alpha0, const float* alpha1, const float* G0, const float* G1, const float* blurred,
+                   float* flow, int h, int w, int dir) {
+    DevBuf a0, a1, g0, g1, bl, f, bnd, tk;
+    const size_t n = (size_t)h * w;
+    RC(a0.upload(alpha0, n * 4)); RC(a1.upload(alpha1, n * 4));
+    RC(g0.upload(G0, n * 8)); RC(g1.upload(G1, n * 8)); RC(bl.upload(blurred, n * 8)); RC(f.upload(flow, n * 8));
+    const size_t lines = pf::sweep_boundary_lines(h, w) + 1;
+    RC(bnd.alloc(lines * 16)); RC(tk.alloc(16));
+    PF_CUDA(cudaMemset(bnd.p, 0, lines * 16)); PF_CUDA(cudaMemset(tk.p, 0, 16));
+    pf::SweepArgs sa;
+    sa.alpha0 = a0.as<float>(); sa.alpha1 = a1.as<float>(); sa.G0 = g0.as<float2>(); sa.G1 = g1.as<float2>();
+    sa.blurred = bl.as<float2>(); sa.flow = f.as<float2>(); sa.h = h; sa.w = w;
+    sa.boundary = bnd.as<uint4>(); sa.ticket = tk.as<int>();
+    pf::launch_sweep(sa, dir, 0);
+    LAUNCHED(1);
+    return f.download(flow, n * 8);
+}
+int pf_stage_upsample_cubic(const float* src, int sh, int sw, float* dst, int dh, int dw) {
+    DevBuf s, d;
+    RC(s.upload(src, (size_t)sh * sw * 8)); RC(d.alloc((size_t)dh * dw * 8));
+    pf::launch_upsample_cubic(s.as<float2>(), sh, sw, d.as<float2>(), dh, dw, 0);
+    LAUNCHED(1);
+    return d.download(dst, (size_t)dh * dw * 8);
+}
+int pf_stage_tail(const float* flow0, int sh, int sw, int rows, int pcols, int pad, int cols, float* out) {
+    DevBuf s, d;
+    RC(s.upload(flow0, (size_t)sh * sw * 8)); RC(d.alloc((size_t)rows * cols * 8));
+    pf::launch_tail(s.as<float2>(), sh, sw, rows, pcols, pad, cols, d.as<float2>(), (size_t)cols * 8, 0);
+    LAUNCHED(1);
+    return d.download(out, (size_t)rows * cols * 8);
+}
+int pf_stage_initial_flow(const float* I0, const float* I1, const float* alpha0, const float* alpha1, float* flow,
+                          int h, int w, int hint, int dist) {
+    DevBuf i0, i1, a0, a1, f, r;
+    const size_t n = (size_t)h * w;
+    RC(i0.upload(I0, n * 4)); RC(i1.upload(I1, n * 4)); RC(a0.upload(alpha0, n * 4)); RC(a1.upload(alpha1, n * 4));
+    RC(f.alloc(n * 8)); RC(r.alloc(16));
+    pf::launch_initial_flow(i0.as<float>(), i1.as<float>(), a0.as<float>(), a1.as<float>(), f.as<float2>(), r.as<float>(), h, w, hint, dist, 0);
+    LAUNCHED(2);
+    return f.download(flow, n * 8);
+}
+
+}  // extern "C"

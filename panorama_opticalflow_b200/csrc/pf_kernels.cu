@@ -1,0 +1,642 @@
+// pf_kernels.cu -- hand-written sm_100a kernels of the PixFlow hot path (round-1 layout: row-major).
+//
+// Arithmetic contract: every kernel is bit-compatible with the reference CPU path (CPU/PixFlow.hpp,
+// CPU/OpticalFlow.cpp and the OpenCV primitives they call).  Compile with
+// -fmad=false; never --use_fast_math.
+#include "pf_kernels.cuh"
+#include "pf_math.cuh"
+
+namespace pf {
+
+static inline dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
+
+// ====================================================================================================
+// front end
+// ====================================================================================================
+__device__ __forceinline__ int sat_short_rint(float v) {
+    int r = __float2int_rn(v);
+    return r < -32768 ? -32768 : (r > 32767 ? 32767 : r);
+}
+
+__global__ void __launch_bounds__(256)
+k_frontend_resize(const uint8_t* __restrict__ bgra, size_t stride, int rows, int cols, int pad,
+                  float* __restrict__ grey, float* __restrict__ alpha, int dh, int dw,
+                  double scale_x, double scale_y) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int pcols = cols + 2 * pad;
+    int sx, sy, ia[4], ib[4];
+    {
+        float f, c[4];
+        resize_coord(x, scale_x, sx, f);
+        cubic_coeffs(f, c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ia[k] = sat_short_rint(fmul(c[k], 2048.0f));
+        resize_coord(y, scale_y, sy, f);
+        cubic_coeffs(f, c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ib[k] = sat_short_rint(fmul(c[k], 2048.0f));
+    }
+    int scol[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int sc = clampi(sx - 1 + j, 0, pcols - 1) - pad;   // circular pad of prepare()
+        if (sc < 0) sc += cols; else if (sc >= cols) sc -= cols;
+        scol[j] = sc;
+    }
+    int hs[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint8_t* S = bgra + (size_t)clampi(sy - 1 + k, 0, rows - 1) * stride;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uchar4 p = *reinterpret_cast<const uchar4*>(S + (size_t)scol[j] * 4);
+            a0 += p.x * ia[j]; a1 += p.y * ia[j]; a2 += p.z * ia[j]; a3 += p.w * ia[j];
+        }
+        hs[k][0] = a0; hs[k][1] = a1; hs[k][2] = a2; hs[k][3] = a3;
+    }
+    // vertical pass: float form for the first n - n%8 bytes of the row, integer form for the tail
+    const int n = dw * 4, nv = n - n % 8;
+    const float sc = 1.0f / 4194304.0f;
+    const float b0 = fmul((float)ib[0], sc), b1 = fmul((float)ib[1], sc), b2 = fmul((float)ib[2], sc), b3 = fmul((float)ib[3], sc);
+    int px[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        int v;
+        if (x * 4 + c < nv) {
+            const float t = fadd(fadd(fadd(fmul((float)hs[3][c], b3), fmul((float)hs[2][c], b2)), fmul((float)hs[1][c], b1)), fmul((float)hs[0][c], b0));
+            v = __float2int_rn(t);
+        } else {
+            v = (hs[0][c] * ib[0] + hs[1][c] * ib[1] + hs[2][c] * ib[2] + hs[3][c] * ib[3] + (1 << 21)) >> 22;
+        }
+        px[c] = v < 0 ? 0 : (v > 255 ? 255 : v);
+    }
+    const int g = (px[0] * 3735 + px[1] * 19235 + px[2] * 9798 + 16384) >> 15;   // BGRA2GRAY
+    grey[(size_t)y * dw + x] = fmul((float)g, PF_INV255);
+    alpha[(size_t)y * dw + x] = fmul((float)px[3], PF_INV255);
+}
+
+void launch_frontend_resize(const uint8_t* bgra, size_t stride, int rows, int cols, int pad,
+                            float* grey, float* alpha, int dh, int dw, cudaStream_t st) {
+    const int pcols = cols + 2 * pad;
+    const double scale_x = 1.0 / ((double)dw / (double)pcols);
+    const double scale_y = 1.0 / ((double)dh / (double)rows);
+    dim3 b(32, 8);
+    k_frontend_resize<<<grid2d(dw, dh, b), b, 0, st>>>(bgra, stride, rows, cols, pad, grey, alpha, dh, dw, scale_x, scale_y);
+}
+
+__global__ void __launch_bounds__(256)
+k_gauss5(const float* __restrict__ src, float* __restrict__ dst, int h, int w) {
+    PF_GAUSS_TABLES
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int xm1 = reflect101(x - 1, w), xp1 = reflect101(x + 1, w), xm2 = reflect101(x - 2, w), xp2 = reflect101(x + 2, w);
+    float r[5];
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {
+        const float* S = src + (size_t)reflect101(y + dy, h) * w;
+        float s0 = fmul(S[x], kG5[0]);
+        s0 = fadd(s0, fmul(fadd(S[xm1], S[xp1]), kG5[1]));
+        s0 = fadd(s0, fmul(fadd(S[xm2], S[xp2]), kG5[2]));
+        r[dy + 2] = s0;
+    }
+    float o = fmul(kG5[0], r[2]);
+    o = fadd(o, fmul(kG5[1], fadd(r[3], r[1])));
+    o = fadd(o, fmul(kG5[2], fadd(r[4], r[0])));
+    dst[(size_t)y * w + x] = o;
+    (void)kG3H; (void)kG3O; (void)kG15;
+}
+
+void launch_gauss5(const float* src, float* dst, int h, int w, cudaStream_t st) {
+    dim3 b(32, 8);
+    k_gauss5<<<grid2d(w, h, b), b, 0, st>>>(src, dst, h, w);
+}
+
+// ====================================================================================================
+// pyramid: INTER_LINEAR
+// ====================================================================================================
+__device__ __forceinline__ void linear_coord_x(int d, double scale, int sw, int& s, float& f) {
+    resize_coord(d, scale, s, f);
+    if (s < 0) { s = 0; f = 0.0f; }
+    if (s >= sw - 1) { s = sw - 1; f = 0.0f; }
+}
+
+__global__ void __launch_bounds__(256)
+k_pyr_down(PlaneSet ps, int sh, int sw, int dh, int dw, double scale_x, double scale_y) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const float* __restrict__ src = ps.src[blockIdx.z];
+    float* __restrict__ dst = ps.dst[blockIdx.z];
+    int s, sy; float f, fy;
+    linear_coord_x(x, scale_x, sw, s, f);
+    resize_coord(y, scale_y, sy, fy);
+    const float* S0 = src + (size_t)clampi(sy, 0, sh - 1) * sw;
+    const float* S1 = src + (size_t)clampi(sy + 1, 0, sh - 1) * sw;
+    float r0, r1;
+    if (s >= sw - 1) { r0 = S0[s]; r1 = S1[s]; }
+    else {
+        const float g = fsub(1.0f, f);
+        r0 = fadd(fmul(S0[s], g), fmul(S0[s + 1], f));
+        r1 = fadd(fmul(S1[s], g), fmul(S1[s + 1], f));
+    }
+    dst[(size_t)y * dw + x] = fadd(fmul(r0, fsub(1.0f, fy)), fmul(r1, fy));
+}
+
+void launch_pyr_down(const PlaneSet& ps, int nplanes, int sh, int sw, int dh, int dw, cudaStream_t st) {
+    const double scale_x = 1.0 / ((double)dw / (double)sw);
+    const double scale_y = 1.0 / ((double)dh / (double)sh);
+    dim3 b(32, 8);
+    dim3 g = grid2d(dw, dh, b);
+    g.z = nplanes;
+    k_pyr_down<<<g, b, 0, st>>>(ps, sh, sw, dh, dw, scale_x, scale_y);
+}
+
+// ====================================================================================================
+// gradients: Sobel k=1 (replicate) then 3x3 sigma 0.5 blur (reflect-101), output interleaved (Ix, Iy)
+// ====================================================================================================
+__global__ void __launch_bounds__(256)
+k_gradient(const float* __restrict__ I, float2* __restrict__ G, int h, int w) {
+    PF_GAUSS_TABLES
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    int xs[3] = { reflect101(x - 1, w), x, reflect101(x + 1, w) };
+    float rx[3], ry[3];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = reflect101(y + dy, h);
+        const float* R = I + (size_t)yy * w;
+        const float* Rp = I + (size_t)clampi(yy + 1, 0, h - 1) * w;
+        const float* Rm = I + (size_t)clampi(yy - 1, 0, h - 1) * w;
+        float sx[3], sy[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int xx = xs[k];
+            sx[k] = fsub(R[clampi(xx + 1, 0, w - 1)], R[clampi(xx - 1, 0, w - 1)]);
+            sy[k] = fsub(Rp[xx], Rm[xx]);
+        }
+        rx[dy + 1] = fadd(fmul(sx[1], kG3H[0]), fmul(fadd(sx[0], sx[2]), kG3H[1]));
+        ry[dy + 1] = fadd(fmul(sy[1], kG3H[0]), fmul(fadd(sy[0], sy[2]), kG3H[1]));
+    }
+    float2 o;
+    o.x = fadd(fmul(kG3H[0], rx[1]), fmul(kG3H[1], fadd(rx[2], rx[0])));
+    o.y = fadd(fmul(kG3H[0], ry[1]), fmul(kG3H[1], fadd(ry[2], ry[0])));
+    G[(size_t)y * w + x] = o;
+    (void)kG5; (void)kG3O; (void)kG15;
+}
+
+void launch_gradient(const float* I, float2* G, int h, int w, cudaStream_t st) {
+    dim3 b(32, 8);
+    k_gradient<<<grid2d(w, h, b), b, 0, st>>>(I, G, h, w);
+}
+
+// ====================================================================================================
+// 15x15 sigma 8 blur on float2 (row pass: left-to-right taps; column pass: symmetric form)
+// ====================================================================================================
+__global__ void __launch_bounds__(256)
+k_blur15_rows(const float2* __restrict__ src, float2* __restrict__ tmp, int h, int w) {
+    PF_GAUSS_TABLES
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float2* S = src + (size_t)y * w;
+    float2 v = S[reflect101(x - 7, w)];
+    float sx = fmul(kG15[7], v.x), sy = fmul(kG15[7], v.y);
+#pragma unroll
+    for (int i = 1; i < 15; ++i) {
+        v = S[reflect101(x - 7 + i, w)];
+        const float k = kG15[i < 7 ? 7 - i : i - 7];
+        sx = fadd(sx, fmul(k, v.x));
+        sy = fadd(sy, fmul(k, v.y));
+    }
+    tmp[(size_t)y * w + x] = make_float2(sx, sy);
+    (void)kG5; (void)kG3O; (void)kG3H;
+}
+
+template <bool DIFFUSE>
+__global__ void __launch_bounds__(256)
+k_blur15_cols(const float2* __restrict__ tmp, float2* __restrict__ dst, int h, int w,
+              const float* __restrict__ alpha0, const float* __restrict__ alpha1, const float2* __restrict__ flow) {
+    PF_GAUSS_TABLES
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float2 c = tmp[(size_t)y * w + x];
+    float sx = fmul(kG15[0], c.x), sy = fmul(kG15[0], c.y);
+#pragma unroll
+    for (int i = 1; i <= 7; ++i) {
+        const float2 a = tmp[(size_t)reflect101(y + i, h) * w + x];
+        const float2 b = tmp[(size_t)reflect101(y - i, h) * w + x];
+        sx = fadd(sx, fmul(kG15[i], fadd(a.x, b.x)));
+        sy = fadd(sy, fmul(kG15[i], fadd(a.y, b.y)));
+    }
+    if (DIFFUSE) {   // lowAlphaFlowDiffusion, CPU/PixFlow.hpp:395-404
+        const size_t p = (size_t)y * w + x;
+        const float d = fsub(1.0f, fmul(alpha0[p], alpha1[p]));
+        const float e = fsub(1.0f, d);
+        const float2 f = flow[p];
+        sx = fadd(fmul(d, sx), fmul(e, f.x));
+        sy = fadd(fmul(d, sy), fmul(e, f.y));
+    }
+    dst[(size_t)y * w + x] = make_float2(sx, sy);
+    (void)kG5; (void)kG3O; (void)kG3H;
+}
+
+void launch_blur15_rows(const float2* src, float2* tmp, int h, int w, cudaStream_t st) {
+    dim3 b(32, 8);
+    k_blur15_rows<<<grid2d(w, h, b), b, 0, st>>>(src, tmp, h, w);
+}
+
+void launch_blur15_cols(const float2* tmp, float2* dst, int h, int w,
+                        const float* alpha0, const float* alpha1, const float2* flow, cudaStream_t st) {
+    dim3 b(32, 8);
+    if (alpha0) k_blur15_cols<true><<<grid2d(w, h, b), b, 0, st>>>(tmp, dst, h, w, alpha0, alpha1, flow);
+    else k_blur15_cols<false><<<grid2d(w, h, b), b, 0, st>>>(tmp, dst, h, w, nullptr, nullptr, nullptr);
+}
+
+// ====================================================================================================
+// median 5x5 on float2 (replicate border)
+// ====================================================================================================
+__global__ void __launch_bounds__(128)
+k_median5(const float2* __restrict__ src, float2* __restrict__ dst, int h, int w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float vx[25], vy[25];
+    int xs[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) xs[d] = clampi(x + d - 2, 0, w - 1);
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+        const float2* S = src + (size_t)clampi(y + dy - 2, 0, h - 1) * w;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            const float2 v = S[xs[dx]];
+            vx[dy * 5 + dx] = v.x;
+            vy[dy * 5 + dx] = v.y;
+        }
+    }
+    dst[(size_t)y * w + x] = make_float2(median25(vx), median25(vy));
+}
+
+void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st) {
+    dim3 b(32, 4);
+    k_median5<<<grid2d(w, h, b), b, 0, st>>>(src, dst, h, w);
+}
+
+// ====================================================================================================
+// Gauss-Seidel sweep as an anti-diagonal wavefront.
+//
+// The reference visits pixels in raster order (forward) or reverse raster order (backward) and updates
+// the flow in place; a pixel reads only its already-updated left/up (forward) or right/down (backward)
+// neighbours from the array being written, so processing by anti-diagonals is bit-identical.
+// Mapping: one warp per block of 32 logical rows, one lane per row; at step s lane k handles logical
+// column s-k.  The left neighbour is the lane's own previous result, the up neighbour arrives from lane
+// k-1 by shuffle, and lane 0 takes it from the previous row block through an LL-style boundary line
+// {fx, flag, fy, flag} written with a single 16-byte volatile store (each 8-byte half carries its own
+// flag, so no fence -- and hence no L1 invalidation -- is needed).  Row blocks are claimed through an
+// atomic ticket so that block b is always scheduled after block b-1: no deadlock whatever the residency.
+// ====================================================================================================
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(32)
+k_sweep(SweepArgs a) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x;
+    int b = 0;
+    if (lane == 0) b = atomicAdd(a.ticket, 1);
+    b = __shfl_sync(full, b, 0);
+    const int w = a.w, h = a.h;
+    const int j = b * 32 + lane;                 // logical row
+    const bool rowValid = j < h;
+    const int y = DIR > 0 ? j : h - 1 - j;
+    const uint4* bin = b > 0 ? a.boundary + (size_t)(b - 1) * w : nullptr;
+    uint4* bout = ((b + 1) * 32 < h) ? a.boundary + (size_t)b * w : nullptr;
+    ErrCtx c;
+    c.G1 = a.G1; c.w = w; c.h = h;
+    c.wm2 = fsub((float)w, 2.0f); c.hm2 = fsub((float)h, 2.0f); c.fw = (float)w;
+
+    float2 prev = make_float2(0.0f, 0.0f);
+    const int nsteps = w + 31;
+    for (int s = 0; s < nsteps; ++s) {
+        float2 up;
+        up.x = __shfl_up_sync(full, prev.x, 1);
+        up.y = __shfl_up_sync(full, prev.y, 1);
+        if (lane == 0 && bin != nullptr && s < w) {
+            uint4 v = ld_volatile_v4(bin + s);
+            while (v.y != 1u || v.w != 1u) v = ld_volatile_v4(bin + s);
+            up.x = __uint_as_float(v.x);
+            up.y = __uint_as_float(v.z);
+        }
+        const int i = s - lane;                  // logical column
+        if (rowValid && i >= 0 && i < w) {
+            const int x = DIR > 0 ? i : w - 1 - i;
+            const size_t p = (size_t)y * w + x;
+            float2 f = a.flow[p];
+            if (a.alpha0[p] > PF_ALPHA_THRESHOLD && a.alpha1[p] > PF_ALPHA_THRESHOLD) {
+                const float2 g0 = a.G0[p];
+                const float2 bl = a.blurred[p];
+                float cur = error_function(c, x, y, g0, bl, f.x, f.y);
+                if (i > 0) {
+                    const float e = error_function(c, x, y, g0, bl, prev.x, prev.y);
+                    if (e < cur) { f = prev; cur = e; }
+                }
+                if (j > 0) {
+                    const float e = error_function(c, x, y, g0, bl, up.x, up.y);
+                    if (e < cur) { f = up; cur = e; }
+                }
+                const float ex = error_function(c, x, y, g0, bl, fadd(f.x, PF_GRAD_EPS), fadd(f.y, 0.0f));
+                const float ey = error_function(c, x, y, g0, bl, fadd(f.x, 0.0f), fadd(f.y, PF_GRAD_EPS));
+                const float gx = __fdiv_rn(fsub(ex, cur), PF_GRAD_EPS);
+                const float gy = __fdiv_rn(fsub(ey, cur), PF_GRAD_EPS);
+                f.x = fsub(f.x, fmul(PF_GRAD_STEP, gx));
+                f.y = fsub(f.y, fmul(PF_GRAD_STEP, gy));
+                a.flow[p] = f;
+            }
+            prev = f;
+            if (lane == 31 && bout != nullptr)
+                st_volatile_v4(bout + i, make_uint4(__float_as_uint(f.x), 1u, __float_as_uint(f.y), 1u));
+        }
+    }
+}
+
+size_t sweep_boundary_lines(int h, int w) {
+    const int nb = (h + 31) / 32;
+    return (size_t)(nb > 1 ? nb - 1 : 0) * (size_t)w;
+}
+
+void launch_sweep(const SweepArgs& a, int dir, cudaStream_t st) {
+    const int nb = (a.h + 31) / 32;
+    if (dir > 0) k_sweep<1><<<nb, 32, 0, st>>>(a);
+    else k_sweep<-1><<<nb, 32, 0, st>>>(a);
+}
+
+// ====================================================================================================
+// inter-level upsample: INTER_CUBIC on float2, then * (1/0.9)
+// ====================================================================================================
+__global__ void __launch_bounds__(256)
+k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, float2* __restrict__ dst, int dh, int dw,
+                 double scale_x, double scale_y) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    int sx, sy; float f, ca[4], cb[4];
+    resize_coord(x, scale_x, sx, f); cubic_coeffs(f, ca);
+    resize_coord(y, scale_y, sy, f); cubic_coeffs(f, cb);
+    int xs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xs[k] = clampi(sx - 1 + k, 0, sw - 1);
+    float rx[4], ry[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2* S = src + (size_t)clampi(sy - 1 + k, 0, sh - 1) * sw;
+        const float2 v0 = S[xs[0]], v1 = S[xs[1]], v2 = S[xs[2]], v3 = S[xs[3]];
+        rx[k] = fadd(fadd(fadd(fmul(v0.x, ca[0]), fmul(v1.x, ca[1])), fmul(v2.x, ca[2])), fmul(v3.x, ca[3]));
+        ry[k] = fadd(fadd(fadd(fmul(v0.y, ca[0]), fmul(v1.y, ca[1])), fmul(v2.y, ca[2])), fmul(v3.y, ca[3]));
+    }
+    // vertical pass: right-to-left for the first n - n%4 floats of the row, left-to-right for the tail
+    const int n = dw * 2, nv = n - n % 4;
+    float ox, oy;
+    if (2 * x < nv) {
+        ox = fadd(fadd(fadd(fmul(rx[3], cb[3]), fmul(rx[2], cb[2])), fmul(rx[1], cb[1])), fmul(rx[0], cb[0]));
+        oy = fadd(fadd(fadd(fmul(ry[3], cb[3]), fmul(ry[2], cb[2])), fmul(ry[1], cb[1])), fmul(ry[0], cb[0]));
+    } else {
+        ox = fadd(fadd(fadd(fmul(rx[0], cb[0]), fmul(rx[1], cb[1])), fmul(rx[2], cb[2])), fmul(rx[3], cb[3]));
+        oy = fadd(fadd(fadd(fmul(ry[0], cb[0]), fmul(ry[1], cb[1])), fmul(ry[2], cb[2])), fmul(ry[3], cb[3]));
+    }
+    dst[(size_t)y * dw + x] = make_float2(fmul(ox, PF_INV_PYR), fmul(oy, PF_INV_PYR));
+}
+
+void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int dh, int dw, cudaStream_t st) {
+    const double scale_x = 1.0 / ((double)dw / (double)sw);
+    const double scale_y = 1.0 / ((double)dh / (double)sh);
+    dim3 b(32, 8);
+    k_upsample_cubic<<<grid2d(dw, dh, b), b, 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y);
+}
+
+// ====================================================================================================
+// tail: INTER_LINEAR to (rows x pcols), *2, 3x3 sigma 1 blur; writes the cropped columns only
+// ====================================================================================================
+struct LinTap { int s; float f; bool edge; };
+
+__global__ void __launch_bounds__(256)
+k_tail(const float2* __restrict__ src, int sh, int sw, int rows, int pcols, int pad, int cols,
+       float2* __restrict__ out, size_t out_stride, double scale_x, double scale_y) {
+    PF_GAUSS_TABLES
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (xo >= cols || y >= rows) return;
+    const int x = xo + pad;
+    LinTap tx[3];
+    int y0[3], y1[3]; float fy[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int xx = reflect101(x + k - 1, pcols);
+        linear_coord_x(xx, scale_x, sw, tx[k].s, tx[k].f);
+        tx[k].edge = tx[k].s >= sw - 1;
+        const int yy = reflect101(y + k - 1, rows);
+        int sy;
+        resize_coord(yy, scale_y, sy, fy[k]);
+        y0[k] = clampi(sy, 0, sh - 1);
+        y1[k] = clampi(sy + 1, 0, sh - 1);
+    }
+    float rbx[3], rby[3];   // row-blurred values for rows y-1, y, y+1
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float2* S0 = src + (size_t)y0[r] * sw;
+        const float2* S1 = src + (size_t)y1[r] * sw;
+        const float b1 = fy[r], b0 = fsub(1.0f, b1);
+        float ux[3], uy[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float2 r0, r1;
+            const int s = tx[k].s;
+            if (tx[k].edge) { r0 = S0[s]; r1 = S1[s]; }
+            else {
+                const float f = tx[k].f, g = fsub(1.0f, f);
+                const float2 a0 = S0[s], a1 = S0[s + 1], c0 = S1[s], c1 = S1[s + 1];
+                r0.x = fadd(fmul(a0.x, g), fmul(a1.x, f)); r0.y = fadd(fmul(a0.y, g), fmul(a1.y, f));
+                r1.x = fadd(fmul(c0.x, g), fmul(c1.x, f)); r1.y = fadd(fmul(c0.y, g), fmul(c1.y, f));
+            }
+            ux[k] = fmul(fadd(fmul(r0.x, b0), fmul(r1.x, b1)), 2.0f);   // flow *= 1/downscaleFactor
+            uy[k] = fmul(fadd(fmul(r0.y, b0), fmul(r1.y, b1)), 2.0f);
+        }
+        rbx[r] = fadd(fmul(ux[1], kG3O[0]), fmul(fadd(ux[0], ux[2]), kG3O[1]));
+        rby[r] = fadd(fmul(uy[1], kG3O[0]), fmul(fadd(uy[0], uy[2]), kG3O[1]));
+    }
+    float2 o;
+    o.x = fadd(fmul(kG3O[0], rbx[1]), fmul(kG3O[1], fadd(rbx[2], rbx[0])));
+    o.y = fadd(fmul(kG3O[0], rby[1]), fmul(kG3O[1], fadd(rby[2], rby[0])));
+    *reinterpret_cast<float2*>(reinterpret_cast<char*>(out) + (size_t)y * out_stride + (size_t)xo * sizeof(float2)) = o;
+    (void)kG5; (void)kG3H; (void)kG15;
+}
+
+void launch_tail(const float2* flow0, int sh, int sw, int rows, int pcols, int pad, int cols,
+                 float2* out, size_t out_stride, cudaStream_t st) {
+    const double scale_x = 1.0 / ((double)pcols / (double)sw);
+    const double scale_y = 1.0 / ((double)rows / (double)sh);
+    dim3 b(32, 8);
+    k_tail<<<grid2d(cols, rows, b), b, 0, st>>>(flow0, sh, sw, rows, pcols, pad, cols, out, out_stride, scale_x, scale_y);
+}
+
+// ====================================================================================================
+// coarsest-level search
+// ====================================================================================================
+// computeIntensityRatio: sequential fp32 sums in raster order (order-dependent -> one thread)
+__global__ void k_intensity_ratio(const float* __restrict__ I0, const float* __restrict__ a0,
+                                  const float* __restrict__ I1, const float* __restrict__ a1, int n, float* ratio) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float sumL = 0.0f, sumR = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        const float al = fmul(a0[i], a1[i]);
+        sumL = fadd(sumL, fmul(al, I0[i]));
+        sumR = fadd(sumR, fmul(al, I1[i]));
+    }
+    ratio[0] = __fdiv_rn(sumL, sumR);
+}
+
+// computePatchError, CPU/PixFlow.hpp:157-188 (I1eq = I1 * ratio evaluated on the fly)
+__device__ float patch_error(const float* __restrict__ i0, const float* __restrict__ a0, int i0x, int i0y,
+                             const float* __restrict__ i1, const float* __restrict__ a1, int i1x, int i1y,
+                             int w, int h, float ratio, int dist) {
+    float sad = 0.0f, alpha = 0.0f;
+    for (int dy = -2; dy <= 2; ++dy) {
+        const int d0y = i0y + dy;
+        if (0 <= d0y && d0y < h) {
+            const int d1y = clampi(i1y + dy, 0, h - 1);
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int d0x = i0x + dx;
+                if (0 <= d0x && d0x < w) {
+                    const int d1x = clampi(i1x + dx, 0, w - 1);
+                    const float diff = fsub(i0[(size_t)d0y * w + d0x], fmul(i1[(size_t)d1y * w + d1x], ratio));
+                    sad = fadd(sad, fabsf(diff));
+                    alpha = fadd(alpha, fmul(a0[(size_t)d0y * w + d0x], a1[(size_t)d1y * w + d1x]));
+                }
+            }
+        }
+    }
+    sad = __fdiv_rn(sad, alpha);
+    const double fx = (double)(i1x - i0x), fy = (double)(i1y - i0y);
+    const float length = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy))));
+    sad = fmul(sad, fadd(1.0f, __fdiv_rn(length, (float)dist)));
+    return sad;
+}
+
+__global__ void __launch_bounds__(128)
+k_adjust_initial_flow(const float* __restrict__ I0, const float* __restrict__ I1,
+                      const float* __restrict__ a0, const float* __restrict__ a1, float2* __restrict__ flow,
+                      const float* __restrict__ ratio_p, int h, int w, int bx, int by, int bw, int bh, int dist) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float2 out = make_float2(0.0f, 0.0f);
+    if (bw > 0 && a0[(size_t)y * w + x] > PF_ALPHA_THRESHOLD) {
+        const float ratio = ratio_p[0];
+        float errorBest = fmul(0.8f, patch_error(I0, a0, x, y, I1, a1, x, y, w, h, ratio, dist));
+        int bestx = x, besty = y;
+        for (int dy = by; dy < by + bh; ++dy)
+            for (int dx = bx; dx < bx + bw; ++dx) {
+                const int i1x = x + dx, i1y = y + dy;
+                if (0 <= i1x && i1x < w && 0 <= i1y && i1y < h) {
+                    const float e = patch_error(I0, a0, x, y, I1, a1, i1x, i1y, w, h, ratio, dist);
+                    if (errorBest > e) { errorBest = e; bestx = i1x; besty = i1y; }
+                }
+            }
+        out = make_float2((float)(bestx - x), (float)(besty - y));
+    }
+    flow[(size_t)y * w + x] = out;
+}
+
+void launch_initial_flow(const float* I0, const float* I1, const float* alpha0, const float* alpha1,
+                         float2* flow, float* ratio, int h, int w, int hint, int dist, cudaStream_t st) {
+    int bx = 0, by = 0, bw = 0, bh = 0;
+    if (dist > 0 && hint >= 1 && hint <= 4) {   // computeSearchBox, CPU/PixFlow.hpp:207-224
+        const int ortho = (dist + 8 / 2) / 8, thick = 2 * ortho + 1;
+        switch (hint) {
+        case 1: bx = 0; by = -ortho; bw = dist + 1; bh = thick; break;        // RIGHT
+        case 2: bx = -ortho; by = 0; bw = thick; bh = dist + 1; break;        // DOWN
+        case 3: bx = -dist; by = -ortho; bw = dist + 1; bh = thick; break;    // LEFT
+        case 4: bx = -ortho; by = -dist; bw = thick; bh = dist + 1; break;    // UP
+        }
+        k_intensity_ratio<<<1, 32, 0, st>>>(I0, alpha0, I1, alpha1, h * w, ratio);
+    }
+    dim3 b(32, 4);
+    k_adjust_initial_flow<<<grid2d(w, h, b), b, 0, st>>>(I0, I1, alpha0, alpha1, flow, ratio, h, w, bx, by, bw, bh, dist);
+}
+
+// ====================================================================================================
+// combineNovelViews
+// ====================================================================================================
+__device__ __forceinline__ uchar4 novel_view_point(const uint8_t* __restrict__ img, size_t stride, float2 f, double t,
+                                                   int x, int y, int rows, int cols) {
+    int srcx = __double2int_rz(__dadd_rn((double)x, __dmul_rn((double)f.x, t)));
+    if (srcx > cols - 1) srcx -= cols;
+    if (srcx < 0) srcx += cols;
+    int srcy = __double2int_rz(__dadd_rn((double)y, __dmul_rn((double)f.y, t)));
+    if (srcy > rows - 1) srcy = rows - 1;
+    if (srcy < 0) srcy = 0;
+    srcx = clampi(srcx, 0, cols - 1);   // the reference would read out of bounds here; never taken for sane flows
+    return *reinterpret_cast<const uchar4*>(img + (size_t)srcy * stride + (size_t)srcx * 4);
+}
+
+__global__ void __launch_bounds__(256)
+k_combine(const uint8_t* __restrict__ imageL, size_t strideL, const uint8_t* __restrict__ imageR, size_t strideR,
+          const float2* __restrict__ flowLR, size_t strideLR, const float2* __restrict__ flowRL, size_t strideRL,
+          const float* __restrict__ blend, size_t strideB, int rows, int cols, uint8_t* __restrict__ out, size_t strideOut) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const float blendR = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(blend) + (size_t)y * strideB + (size_t)x * 4);
+    const float blendL = fsub(1.0f, blendR);
+    const float2 fLR = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(flowLR) + (size_t)y * strideLR + (size_t)x * 8);
+    const float2 fRL = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(flowRL) + (size_t)y * strideRL + (size_t)x * 8);
+    const uchar4 cL = novel_view_point(imageL, strideL, fRL, (double)blendR, x, y, rows, cols);
+    const uchar4 cR = novel_view_point(imageR, strideR, fLR, (double)blendL, x, y, rows, cols);
+    uchar4 o = make_uchar4(0, 0, 0, 0);
+    if (cL.w != 0 && cR.w != 0) {
+        const float fc = (float)cols;
+        const float magLR = __fdiv_rn(__fsqrt_rn(fadd(fmul(fLR.x, fLR.x), fmul(fLR.y, fLR.y))), fc);
+        const float magRL = __fdiv_rn(__fsqrt_rn(fadd(fmul(fRL.x, fRL.x), fmul(fRL.y, fRL.y))), fc);
+        const int di = abs((int)cL.x - (int)cR.x) + abs((int)cL.y - (int)cR.y) + abs((int)cL.z - (int)cR.z);
+        const float colorDiff = __fdiv_rn((float)di, 255.0f);
+        const float deghost = tanhf(fmul(colorDiff, 10.0f));
+        const float alphaL = __fdiv_rn((float)cL.w, 255.0f), alphaR = __fdiv_rn((float)cR.w, 255.0f);
+        const double aL = (double)fmul(fmul(10.0f, blendL), alphaL);
+        const double aR = (double)fmul(fmul(10.0f, blendR), alphaR);
+        const double expL = exp(__dmul_rn(aL, __dadd_rn(1.0, (double)fmul(100.0f, magRL))));
+        const double expR = exp(__dmul_rn(aR, __dadd_rn(1.0, (double)fmul(100.0f, magLR))));
+        const double sumExp = __dadd_rn(__dadd_rn(expL, expR), 0.00001);
+        const float smL = __double2float_rn(__ddiv_rn(expL, sumExp));
+        const float smR = __double2float_rn(__ddiv_rn(expR, sumExp));
+        const float wL = fadd(fmul(blendL, fsub(1.0f, deghost)), fmul(smL, deghost));   // lerp, util.hpp:98-101
+        const float wR = fadd(fmul(blendR, fsub(1.0f, deghost)), fmul(smR, deghost));
+        o.x = (unsigned char)__float2int_rz(fadd(fmul((float)cL.x, wL), fmul((float)cR.x, wR)));
+        o.y = (unsigned char)__float2int_rz(fadd(fmul((float)cL.y, wL), fmul((float)cR.y, wR)));
+        o.z = (unsigned char)__float2int_rz(fadd(fmul((float)cL.z, wL), fmul((float)cR.z, wR)));
+        o.w = 255;
+    }
+    *reinterpret_cast<uchar4*>(out + (size_t)y * strideOut + (size_t)x * 4) = o;
+}
+
+void launch_combine(const uint8_t* imageL, size_t strideL, const uint8_t* imageR, size_t strideR,
+                    const float2* flowLR, size_t strideLR, const float2* flowRL, size_t strideRL,
+                    const float* blend, size_t strideB, int rows, int cols,
+                    uint8_t* out, size_t strideOut, cudaStream_t st) {
+    dim3 b(32, 8);
+    k_combine<<<grid2d(cols, rows, b), b, 0, st>>>(imageL, strideL, imageR, strideR, flowLR, strideLR, flowRL, strideRL,
+                                                  blend, strideB, rows, cols, out, strideOut);
+}
+
+}  // namespace pf
