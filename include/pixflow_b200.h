@@ -105,6 +105,11 @@ PF_API int pf_set_sweep_timing(pf_engine* engine, int enabled);
 PF_API double pf_last_sweep_ms(pf_engine* engine);
 PF_API uint64_t pf_last_sweep_launches(pf_engine* engine);
 
+/* Device-side stopwatch for benchmarks: CUDA events recorded on a stream of the engine.  start() stamps the
+ * device clock now; stop() waits for every stream of the engine, stamps again and returns the elapsed ms. */
+PF_API int pf_timer_start(pf_engine* engine);
+PF_API int pf_timer_stop(pf_engine* engine, double* elapsed_ms);
+
 /* Message of the last error on the calling thread ("" if none).  Replaces exception::what(). */
 PF_API const char* pf_last_error(void);
 PF_API const char* pf_version(void);

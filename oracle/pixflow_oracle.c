@@ -23,6 +23,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef __SSE2__
+#include <emmintrin.h>
+#endif
 
 #define ORC_API __attribute__((visibility("default")))
 
@@ -55,47 +58,53 @@ ORC_API void orc_gaussian_kernel(int k, double sigma, float* out) {
 }
 
 /* GaussianBlur(src, dst, (k,k), sigma), fp32, ch interleaved channels, reflect-101.
- * Row pass: k<=5 symmetric-small form, k>5 left-to-right; column pass symmetric form. */
+ * Row pass: k<=5 symmetric-small form, k>5 left-to-right; column pass symmetric form.
+ * (Rows are reflect-padded once so that the inner loops are branch-free; the order of the floating-point
+ * operations is exactly the one described above.) */
 ORC_API void orc_gaussian_blur(const float* src, int h, int w, int ch, int k, double sigma, float* dst) {
     float kern[64];
     orc_gaussian_kernel(k, sigma, kern);
     const int r = k / 2;
-    const size_t n = (size_t)h * w * ch;
+    const int wc = w * ch;
+    const size_t n = (size_t)h * wc;
     float* tmp = (float*)malloc(n * sizeof(float));
+    float* pad = (float*)malloc(sizeof(float) * (size_t)(w + 2 * r) * ch);
     for (int y = 0; y < h; ++y) {
-        const float* S = src + (size_t)y * w * ch;
-        float* D = tmp + (size_t)y * w * ch;
-        for (int x = 0; x < w; ++x) {
-            for (int c = 0; c < ch; ++c) {
-                float s0;
-                if (k <= 5) {
-                    s0 = S[x * ch + c] * kern[r];
-                    for (int i = 1; i <= r; ++i) {
-                        float a = S[reflect101(x - i, w) * ch + c];
-                        float b = S[reflect101(x + i, w) * ch + c];
-                        s0 = s0 + (a + b) * kern[r + i];
-                    }
-                } else {
-                    s0 = kern[0] * S[reflect101(x - r, w) * ch + c];
-                    for (int i = 1; i < k; ++i)
-                        s0 = s0 + kern[i] * S[reflect101(x - r + i, w) * ch + c];
-                }
-                D[x * ch + c] = s0;
+        const float* S = src + (size_t)y * wc;
+        float* D = tmp + (size_t)y * wc;
+        for (int x = -r; x < w + r; ++x) {
+            const int sx = reflect101(x, w);
+            for (int c = 0; c < ch; ++c) pad[(x + r) * ch + c] = S[sx * ch + c];
+        }
+        const float* P = pad + r * ch; /* P[i] == S[i] for 0 <= i < wc, reflect-extended outside */
+        if (k <= 5) {
+            for (int i = 0; i < wc; ++i) D[i] = P[i] * kern[r];
+            for (int t = 1; t <= r; ++t) {
+                const float kt = kern[r + t];
+                const int o = t * ch;
+                for (int i = 0; i < wc; ++i) D[i] = D[i] + (P[i - o] + P[i + o]) * kt;
+            }
+        } else {
+            const float k0 = kern[0];
+            for (int i = 0; i < wc; ++i) D[i] = k0 * P[i - r * ch];
+            for (int t = 1; t < k; ++t) {
+                const float kt = kern[t];
+                const int o = (t - r) * ch;
+                for (int i = 0; i < wc; ++i) D[i] = D[i] + kt * P[i + o];
             }
         }
     }
-    const int wc = w * ch;
+    free(pad);
     for (int y = 0; y < h; ++y) {
         float* D = dst + (size_t)y * wc;
         const float* C = tmp + (size_t)y * wc;
-        for (int x = 0; x < wc; ++x) {
-            float s0 = kern[r] * C[x] + 0.0f;
-            for (int i = 1; i <= r; ++i) {
-                float a = tmp[(size_t)reflect101(y + i, h) * wc + x];
-                float b = tmp[(size_t)reflect101(y - i, h) * wc + x];
-                s0 = s0 + kern[r + i] * (a + b);
-            }
-            D[x] = s0;
+        const float kc = kern[r];
+        for (int x = 0; x < wc; ++x) D[x] = kc * C[x] + 0.0f;
+        for (int t = 1; t <= r; ++t) {
+            const float* A = tmp + (size_t)reflect101(y + t, h) * wc;
+            const float* B = tmp + (size_t)reflect101(y - t, h) * wc;
+            const float kt = kern[r + t];
+            for (int x = 0; x < wc; ++x) D[x] = D[x] + kt * (A[x] + B[x]);
         }
     }
     free(tmp);
@@ -117,31 +126,52 @@ ORC_API void orc_sobel(const float* src, int h, int w, int dx, float* dst) {
         }
 }
 
-static int cmp_float(const void* a, const void* b) {
-    float x = *(const float*)a, y = *(const float*)b;
-    return (x > y) - (x < y);
-}
+/* 99-comparator median-of-25 selection network (Devillard's opt_med25; verified exhaustively with the 0-1
+ * principle).  Pure min/max selection, so the result equals the median whatever the algorithm. */
+static const unsigned char MED25_NET[99][2] = {
+{0,1},{3,4},{2,4},{2,3},{6,7},{5,7},{5,6},{9,10},{8,10},{8,9},{12,13},{11,13},{11,12},{15,16},{14,16},{14,15},{18,19},{17,19},
+{17,18},{21,22},{20,22},{20,21},{23,24},{2,5},{3,6},{0,6},{0,3},{4,7},{1,7},{1,4},{11,14},{8,14},{8,11},{12,15},{9,15},{9,12},
+{13,16},{10,16},{10,13},{20,23},{17,23},{17,20},{21,24},{18,24},{18,21},{19,22},{8,17},{9,18},{0,18},{0,9},{10,19},{1,19},{1,10},
+{11,20},{2,20},{2,11},{12,21},{3,21},{3,12},{13,22},{4,22},{4,13},{14,23},{5,23},{5,14},{15,24},{6,24},{6,15},{7,16},{7,19},
+{13,21},{15,23},{7,13},{7,15},{1,9},{3,11},{5,17},{11,17},{9,17},{4,10},{6,12},{7,14},{4,6},{4,7},{12,14},{10,14},{6,7},{10,12},
+{6,10},{6,17},{12,17},{7,17},{7,10},{12,18},{7,12},{10,18},{12,20},{10,20},{10,12}};
 
 /* medianBlur(32FC2, 5): per-channel median of the replicated 5x5 window */
 ORC_API void orc_median5_c2(const float* src, int h, int w, float* dst) {
-    float v[25];
-    for (int y = 0; y < h; ++y)
-        for (int x = 0; x < w; ++x)
-            for (int c = 0; c < 2; ++c) {
-                int n = 0;
-                for (int dy = -2; dy <= 2; ++dy)
-                    for (int dx = -2; dx <= 2; ++dx)
-                        v[n++] = src[((size_t)clampi(y + dy, 0, h - 1) * w + clampi(x + dx, 0, w - 1)) * 2 + c];
-                /* partial selection sort up to the median */
-                for (int i = 0; i <= 12; ++i) {
-                    int m = i;
-                    for (int j = i + 1; j < 25; ++j)
-                        if (v[j] < v[m]) m = j;
-                    float t = v[i]; v[i] = v[m]; v[m] = t;
-                }
-                dst[((size_t)y * w + x) * 2 + c] = v[12];
+    const int n = 2 * w;
+    float* v = (float*)malloc(sizeof(float) * 25 * (size_t)n);
+    float* pad = (float*)malloc(sizeof(float) * (size_t)(n + 8));
+    for (int y = 0; y < h; ++y) {
+        for (int dy = -2; dy <= 2; ++dy) {
+            const float* S = src + (size_t)clampi(y + dy, 0, h - 1) * n;
+            for (int x = -2; x < w + 2; ++x) {
+                const int sx = clampi(x, 0, w - 1);
+                pad[(x + 2) * 2] = S[sx * 2];
+                pad[(x + 2) * 2 + 1] = S[sx * 2 + 1];
             }
-    (void)cmp_float;
+            for (int dx = 0; dx < 5; ++dx)
+                memcpy(v + (size_t)((dy + 2) * 5 + dx) * n, pad + 2 * dx, sizeof(float) * n);
+        }
+        for (int c = 0; c < 99; ++c) {
+            float* a = v + (size_t)MED25_NET[c][0] * n;
+            float* b = v + (size_t)MED25_NET[c][1] * n;
+            int i = 0;
+#ifdef __SSE2__
+            for (; i + 4 <= n; i += 4) { /* baseline x86-64 SIMD, like OpenCV's own medianBlur */
+                const __m128 x0 = _mm_loadu_ps(a + i), x1 = _mm_loadu_ps(b + i);
+                _mm_storeu_ps(a + i, _mm_min_ps(x1, x0));
+                _mm_storeu_ps(b + i, _mm_max_ps(x1, x0));
+            }
+#endif
+            for (; i < n; ++i) {
+                const float x0 = a[i], x1 = b[i];
+                a[i] = x1 < x0 ? x1 : x0;
+                b[i] = x1 < x0 ? x0 : x1;
+            }
+        }
+        memcpy(dst + (size_t)y * n, v + (size_t)12 * n, sizeof(float) * n);
+    }
+    free(v); free(pad);
 }
 
 /* cvtColor(BGRA2GRAY) u8, OpenCV 4.x 15-bit coefficients */

@@ -167,6 +167,14 @@ class PixFlow(OpticalFlowInterface):
     def setSweepTiming(self, enabled):
         _lib.check(self._lib.pf_set_sweep_timing(self._h, int(bool(enabled))))
 
+    def timerStart(self):
+        _lib.check(self._lib.pf_timer_start(self._h))
+
+    def timerStop(self):
+        ms = C.c_double()
+        _lib.check(self._lib.pf_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def lastSweepMs(self):
         return float(self._lib.pf_last_sweep_ms(self._h)), int(self._lib.pf_last_sweep_launches(self._h))
 

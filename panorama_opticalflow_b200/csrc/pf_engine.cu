@@ -161,8 +161,15 @@ struct pf_engine {
     uint64_t last_sweep_launches = 0;
     std::mutex mu;
     std::vector<Workspace*> pool;
+    cudaStream_t sTimer = nullptr;
+    cudaEvent_t evT0 = nullptr, evT1 = nullptr;
 
-    ~pf_engine() { for (auto* w : pool) delete w; }
+    ~pf_engine() {
+        for (auto* w : pool) delete w;
+        if (evT0) cudaEventDestroy(evT0);
+        if (evT1) cudaEventDestroy(evT1);
+        if (sTimer) cudaStreamDestroy(sTimer);
+    }
 
     // workspace #idx for the given geometry (created or re-created on demand)
     int workspace(int idx, int rows, int cols, int pad, Workspace** out) {
@@ -402,6 +409,38 @@ int pf_set_sweep_timing(pf_engine* e, int enabled) {
 }
 double pf_last_sweep_ms(pf_engine* e) { return e ? e->last_sweep_ms : 0.0; }
 uint64_t pf_last_sweep_launches(pf_engine* e) { return e ? e->last_sweep_launches : 0; }
+
+int pf_timer_start(pf_engine* e) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    if (!e->sTimer) {
+        PF_CUDA(cudaStreamCreateWithFlags(&e->sTimer, cudaStreamNonBlocking));
+        PF_CUDA(cudaEventCreate(&e->evT0));
+        PF_CUDA(cudaEventCreate(&e->evT1));
+    }
+    PF_CUDA(cudaDeviceSynchronize());
+    PF_CUDA(cudaEventRecord(e->evT0, e->sTimer));
+    return PF_OK;
+}
+
+int pf_timer_stop(pf_engine* e, double* ms) {
+    if (!e || !ms) return fail(PF_ERR_INVALID_ARGUMENT, "engine or elapsed_ms is NULL");
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    if (!e->sTimer) return fail(PF_ERR_INVALID_ARGUMENT, "pf_timer_start was not called");
+    for (Workspace* w : e->pool) {
+        if (!w) continue;
+        PF_CUDA(cudaStreamSynchronize(w->sMain));
+        for (int d = 0; d < 2; ++d) PF_CUDA(cudaStreamSynchronize(w->sDir[d]));
+    }
+    PF_CUDA(cudaEventRecord(e->evT1, e->sTimer));
+    PF_CUDA(cudaEventSynchronize(e->evT1));
+    float f = 0.0f;
+    PF_CUDA(cudaEventElapsedTime(&f, e->evT0, e->evT1));
+    *ms = f;
+    return PF_OK;
+}
 
 int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, size_t s1, int rows, int cols, int hint,
                     void* flow_out, size_t flow_stride) {

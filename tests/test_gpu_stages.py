@@ -48,7 +48,8 @@ def test_frontend(orc, shape, pad):
 def test_pyr_down(orc, shape):
     from panorama_opticalflow_b200 import stages
     a = RNG.random(shape).astype(np.float32)
-    (nw, nh) = orc.pyramid_sizes(shape[1], shape[0])[1]
+    nw = int(np.float32(shape[1]) * np.float32(0.9) + np.float32(0.5))
+    nh = int(np.float32(shape[0]) * np.float32(0.9) + np.float32(0.5))
     assert_bit_equal(stages.pyr_down(a, nh, nw), orc.resize_linear(a, nh, nw), "pyr_down")
 
 
