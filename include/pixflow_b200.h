@@ -129,6 +129,11 @@ PF_API int pf_stage_tail(const float* flow0, int sh, int sw, int rows, int pcols
 PF_API int pf_stage_initial_flow(const float* I0, const float* I1, const float* alpha0, const float* alpha1,
                                  float* flow, int h, int w, int hint, int dist);
 
+/* Exhaustive on-device check of the branch-free exactly-rounded sqrt and division-by-constant used by the sweep
+ * kernels, over every float in their validity range and every integer divisor in [wmin, wmax] (image widths).
+ * out[0] = sqrt mismatches, out[1] = x/0.001f mismatches, out[2] = x/float(w) mismatches, out[3] = first bad w. */
+PF_API int pf_selftest_exact_math(int wmin, int wmax, uint64_t* out4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pf_last_sweep_launches": (C.c_uint64, [_vp]),
     "pf_timer_start": (_i, [_vp]),
     "pf_timer_stop": (_i, [_vp, C.POINTER(C.c_double)]),
+    "pf_selftest_exact_math": (_i, [_i, _i, C.POINTER(C.c_uint64)]),
     "pf_last_error": (C.c_char_p, []),
     "pf_version": (C.c_char_p, []),
     "pf_stage_frontend": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i]),

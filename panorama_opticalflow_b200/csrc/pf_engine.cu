@@ -52,12 +52,15 @@ struct Plan {
     size_t total_px = 0;
     std::vector<size_t> bnd_off;   // per (level, sweep) offset in uint4 lines
     size_t bnd_lines = 0;
+    std::vector<pf::Skew> skew;    // per-level skewed layout
+    std::vector<size_t> skew_off;  // element offset of each level in the skewed gradient pyramids
+    size_t skew_total = 0;
 
     void build(int rows_, int cols_, int pad_) {
         rows = rows_; cols = cols_; pad = pad_; pcols = cols + 2 * pad;
         dw = (int)((float)pcols * 0.5f);
         dh = (int)((float)rows * 0.5f);
-        ws.clear(); hs.clear(); off.clear(); bnd_off.clear();
+        ws.clear(); hs.clear(); off.clear(); bnd_off.clear(); skew.clear(); skew_off.clear();
         ws.push_back(dw); hs.push_back(dh);
         while (ws.size() < 1000) {
             const int nw = (int)((float)ws.back() * 0.9f + 0.5f);
@@ -68,12 +71,16 @@ struct Plan {
         L = (int)ws.size();
         total_px = 0;
         bnd_lines = 0;
+        skew_total = 0;
         for (int l = 0; l < L; ++l) {
             off.push_back(total_px);
             total_px += ((size_t)ws[l] * hs[l] + 63) & ~(size_t)63;   // keep every level 256-byte aligned
+            skew.push_back(pf::make_skew(ws[l], hs[l]));
+            skew_off.push_back(skew_total);
+            skew_total += (pf::skew_elems(skew.back()) + 63) & ~(size_t)63;
             for (int s = 0; s < 2; ++s) {
                 bnd_off.push_back(bnd_lines);
-                bnd_lines += pf::sweep_boundary_lines(hs[l], ws[l]);
+                bnd_lines += pf::sweep2_boundary_lines(hs[l], ws[l], pf::sweep2_use_smem(ws[l]));
             }
         }
     }
@@ -86,7 +93,9 @@ struct Workspace {
     float* I[2] = {nullptr, nullptr};
     float* A[2] = {nullptr, nullptr};
     float* Ipre = nullptr;
-    float2* G[2] = {nullptr, nullptr};
+    float2* G[2] = {nullptr, nullptr};            // row-major gradient pyramids (Ix, Iy)
+    float2* Gs[2] = {nullptr, nullptr};           // the same in the skewed layout (gathered by the sweeps)
+    pf::SweepRec* rec[2] = {nullptr, nullptr};    // per direction: wavefront-packed records of the current sweep
     float2* bufA[2] = {nullptr, nullptr};         // per direction: flow ping
     float2* bufB[2] = {nullptr, nullptr};         // flow pong
     float2* bufT[2] = {nullptr, nullptr};         // blur row-pass temp
@@ -105,7 +114,8 @@ struct Workspace {
     ~Workspace() { release(); }
     void release() {
         for (int k = 0; k < 2; ++k) {
-            cudaFree(in[k]); cudaFree(I[k]); cudaFree(A[k]); cudaFree(G[k]);
+            cudaFree(in[k]); cudaFree(I[k]); cudaFree(A[k]); cudaFree(G[k]); cudaFree(Gs[k]); cudaFree(rec[k]);
+            Gs[k] = nullptr; rec[k] = nullptr;
             cudaFree(bufA[k]); cudaFree(bufB[k]); cudaFree(bufT[k]); cudaFree(blurred[k]);
             cudaFree(ratio[k]); cudaFree(bnd[k]); cudaFree(tickets[k]); cudaFree(out[k]);
             in[k] = nullptr; I[k] = A[k] = nullptr; G[k] = nullptr; bufA[k] = bufB[k] = bufT[k] = blurred[k] = nullptr;
@@ -132,6 +142,8 @@ struct Workspace {
             PF_CUDA(cudaMalloc(&I[k], p.total_px * sizeof(float)));
             PF_CUDA(cudaMalloc(&A[k], p.total_px * sizeof(float)));
             PF_CUDA(cudaMalloc(&G[k], p.total_px * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&Gs[k], p.skew_total * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&rec[k], pf::sweep_rec_count(p.dh, p.dw) * sizeof(pf::SweepRec)));
             PF_CUDA(cudaMalloc(&bufA[k], px0 * sizeof(float2)));
             PF_CUDA(cudaMalloc(&bufB[k], px0 * sizeof(float2)));
             PF_CUDA(cudaMalloc(&bufT[k], px0 * sizeof(float2)));
@@ -221,7 +233,8 @@ int enqueue_shared(pf_engine* e, Workspace& w, const uint8_t* img[2], const size
     for (int l = 0; l < p.L; ++l)
         for (int k = 0; k < 2; ++k) {
             pf::launch_gradient(w.I[k] + p.off[l], w.G[k] + p.off[l], p.hs[l], p.ws[l], w.sMain);
-            LAUNCHED(1);
+            pf::launch_skew_copy_f2(w.G[k] + p.off[l], w.Gs[k] + p.skew_off[l], p.skew[l], w.sMain);
+            LAUNCHED(2);
         }
     PF_CUDA(cudaGetLastError());
     PF_CUDA(cudaEventRecord(w.evReady, w.sMain));
@@ -250,31 +263,36 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
         }
         pf::launch_blur15_rows(flow, w.bufT[d], h, wd, st);
         pf::launch_blur15_cols(w.bufT[d], w.blurred[d], h, wd, nullptr, nullptr, nullptr, st);
-        pf::SweepArgs sa;
-        sa.alpha0 = A0; sa.alpha1 = A1;
-        sa.G0 = w.G[i0] + p.off[l]; sa.G1 = w.G[i1] + p.off[l];
-        sa.blurred = w.blurred[d];
-        sa.h = h; sa.w = wd;
+        const float2* G0 = w.G[i0] + p.off[l];
+        const float2* G1 = w.G[i1] + p.off[l];
+        pf::Sweep2Args sa;
+        sa.rec = w.rec[d];
+        sa.G1s = w.Gs[i1] + p.skew_off[l];
+        sa.s = p.skew[l];
+        sa.g1s_last = (long long)pf::skew_elems(p.skew[l]) - 1;
+        sa.smem_ll = pf::sweep2_use_smem(wd) ? 1 : 0;
         // forward sweep, in place on `flow`
+        pf::launch_sweep_prep(A0, A1, G0, G1, w.blurred[d], flow, w.rec[d], h, wd, +1, st);
         sa.flow = flow;
         sa.boundary = w.bnd[d] + p.bnd_off[2 * l];
         sa.ticket = w.tickets[d] + 2 * l;
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
-        pf::launch_sweep(sa, +1, st);
+        pf::launch_sweep2(sa, +1, st);
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
         pf::launch_median5(flow, other, h, wd, st);
         // backward sweep, in place on `other`
+        pf::launch_sweep_prep(A0, A1, G0, G1, w.blurred[d], other, w.rec[d], h, wd, -1, st);
         sa.flow = other;
         sa.boundary = w.bnd[d] + p.bnd_off[2 * l + 1];
         sa.ticket = w.tickets[d] + 2 * l + 1;
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
-        pf::launch_sweep(sa, -1, st);
+        pf::launch_sweep2(sa, -1, st);
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
         pf::launch_median5(other, flow, h, wd, st);
         // lowAlphaFlowDiffusion: blur + blend, written to `other`
         pf::launch_blur15_rows(flow, w.bufT[d], h, wd, st);
         pf::launch_blur15_cols(w.bufT[d], other, h, wd, A0, A1, flow, st);
-        LAUNCHED(8);
+        LAUNCHED(10);
         if (l > 0) {
             pf::launch_upsample_cubic(other, h, wd, flow, p.hs[l - 1], p.ws[l - 1], st);
             LAUNCHED(1);
@@ -594,6 +612,15 @@ int pf_novel_view(pf_engine* e, const void* L, size_t sl, const void* R, size_t 
     return collect_sweep_timing(e, used);
 }
 
+int pf_selftest_exact_math(int wmin, int wmax, uint64_t* out4) {
+    if (!out4 || wmin < 1 || wmax < wmin) return fail(PF_ERR_INVALID_ARGUMENT, "bad selftest arguments");
+    unsigned long long a = 0, b = 0, c = 0;
+    int first = 0;
+    if (pf::selftest_exact_math(wmin, wmax, &a, &b, &c, &first) != 0) return fail(PF_ERR_CUDA, "selftest failed to run");
+    out4[0] = a; out4[1] = b; out4[2] = c; out4[3] = (uint64_t)first;
+    return PF_OK;
+}
+
 int pf_host_alloc(void** p, size_t bytes) {
     if (!p) return fail(PF_ERR_INVALID_ARGUMENT, "ptr is NULL");
     PF_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
@@ -675,19 +702,25 @@ int pf_stage_median5(const float* flow, float* dst, int h, int w) {
 }
 int pf_stage_sweep(const float* alpha0, const float* alpha1, const float* G0, const float* G1, const float* blurred,
                    float* flow, int h, int w, int dir) {
-    DevBuf a0, a1, g0, g1, bl, f, bnd, tk;
+    DevBuf a0, a1, g0, g1, g1s, bl, f, ra, bnd, tk;
     const size_t n = (size_t)h * w;
+    const pf::Skew sk = pf::make_skew(w, h);
+    const size_t ne = pf::skew_elems(sk);
     RC(a0.upload(alpha0, n * 4)); RC(a1.upload(alpha1, n * 4));
     RC(g0.upload(G0, n * 8)); RC(g1.upload(G1, n * 8)); RC(bl.upload(blurred, n * 8)); RC(f.upload(flow, n * 8));
-    const size_t lines = pf::sweep_boundary_lines(h, w) + 1;
+    RC(g1s.alloc(ne * 8)); RC(ra.alloc(pf::sweep_rec_count(h, w) * sizeof(pf::SweepRec)));
+    const bool sm = pf::sweep2_use_smem(w);
+    const size_t lines = pf::sweep2_boundary_lines(h, w, sm);
     RC(bnd.alloc(lines * 16)); RC(tk.alloc(16));
     PF_CUDA(cudaMemset(bnd.p, 0, lines * 16)); PF_CUDA(cudaMemset(tk.p, 0, 16));
-    pf::SweepArgs sa;
-    sa.alpha0 = a0.as<float>(); sa.alpha1 = a1.as<float>(); sa.G0 = g0.as<float2>(); sa.G1 = g1.as<float2>();
-    sa.blurred = bl.as<float2>(); sa.flow = f.as<float2>(); sa.h = h; sa.w = w;
-    sa.boundary = bnd.as<uint4>(); sa.ticket = tk.as<int>();
-    pf::launch_sweep(sa, dir, 0);
-    LAUNCHED(1);
+    pf::launch_skew_copy_f2(g1.as<float2>(), g1s.as<float2>(), sk, 0);
+    pf::launch_sweep_prep(a0.as<float>(), a1.as<float>(), g0.as<float2>(), g1.as<float2>(), bl.as<float2>(), f.as<float2>(),
+                          ra.as<pf::SweepRec>(), h, w, dir, 0);
+    pf::Sweep2Args sa;
+    sa.rec = ra.as<pf::SweepRec>(); sa.G1s = g1s.as<float2>(); sa.flow = f.as<float2>();
+    sa.s = sk; sa.g1s_last = (long long)ne - 1; sa.boundary = bnd.as<uint4>(); sa.ticket = tk.as<int>(); sa.smem_ll = sm ? 1 : 0;
+    pf::launch_sweep2(sa, dir, 0);
+    LAUNCHED(3);
     return f.download(flow, n * 8);
 }
 int pf_stage_upsample_cubic(const float* src, int sh, int sw, float* dst, int dh, int dw) {

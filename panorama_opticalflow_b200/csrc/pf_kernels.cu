@@ -289,101 +289,6 @@ void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t s
 }
 
 // ====================================================================================================
-// Gauss-Seidel sweep as an anti-diagonal wavefront.
-//
-// The reference visits pixels in raster order (forward) or reverse raster order (backward) and updates
-// the flow in place; a pixel reads only its already-updated left/up (forward) or right/down (backward)
-// neighbours from the array being written, so processing by anti-diagonals is bit-identical.
-// Mapping: one warp per block of 32 logical rows, one lane per row; at step s lane k handles logical
-// column s-k.  The left neighbour is the lane's own previous result, the up neighbour arrives from lane
-// k-1 by shuffle, and lane 0 takes it from the previous row block through an LL-style boundary line
-// {fx, flag, fy, flag} written with a single 16-byte volatile store (each 8-byte half carries its own
-// flag, so no fence -- and hence no L1 invalidation -- is needed).  Row blocks are claimed through an
-// atomic ticket so that block b is always scheduled after block b-1: no deadlock whatever the residency.
-// ====================================================================================================
-__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-template <int DIR>
-__global__ void __launch_bounds__(32)
-k_sweep(SweepArgs a) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
-    int b = 0;
-    if (lane == 0) b = atomicAdd(a.ticket, 1);
-    b = __shfl_sync(full, b, 0);
-    const int w = a.w, h = a.h;
-    const int j = b * 32 + lane;                 // logical row
-    const bool rowValid = j < h;
-    const int y = DIR > 0 ? j : h - 1 - j;
-    const uint4* bin = b > 0 ? a.boundary + (size_t)(b - 1) * w : nullptr;
-    uint4* bout = ((b + 1) * 32 < h) ? a.boundary + (size_t)b * w : nullptr;
-    ErrCtx c;
-    c.G1 = a.G1; c.w = w; c.h = h;
-    c.wm2 = fsub((float)w, 2.0f); c.hm2 = fsub((float)h, 2.0f); c.fw = (float)w;
-
-    float2 prev = make_float2(0.0f, 0.0f);
-    const int nsteps = w + 31;
-    for (int s = 0; s < nsteps; ++s) {
-        float2 up;
-        up.x = __shfl_up_sync(full, prev.x, 1);
-        up.y = __shfl_up_sync(full, prev.y, 1);
-        if (lane == 0 && bin != nullptr && s < w) {
-            uint4 v = ld_volatile_v4(bin + s);
-            while (v.y != 1u || v.w != 1u) v = ld_volatile_v4(bin + s);
-            up.x = __uint_as_float(v.x);
-            up.y = __uint_as_float(v.z);
-        }
-        const int i = s - lane;                  // logical column
-        if (rowValid && i >= 0 && i < w) {
-            const int x = DIR > 0 ? i : w - 1 - i;
-            const size_t p = (size_t)y * w + x;
-            float2 f = a.flow[p];
-            if (a.alpha0[p] > PF_ALPHA_THRESHOLD && a.alpha1[p] > PF_ALPHA_THRESHOLD) {
-                const float2 g0 = a.G0[p];
-                const float2 bl = a.blurred[p];
-                float cur = error_function(c, x, y, g0, bl, f.x, f.y);
-                if (i > 0) {
-                    const float e = error_function(c, x, y, g0, bl, prev.x, prev.y);
-                    if (e < cur) { f = prev; cur = e; }
-                }
-                if (j > 0) {
-                    const float e = error_function(c, x, y, g0, bl, up.x, up.y);
-                    if (e < cur) { f = up; cur = e; }
-                }
-                const float ex = error_function(c, x, y, g0, bl, fadd(f.x, PF_GRAD_EPS), fadd(f.y, 0.0f));
-                const float ey = error_function(c, x, y, g0, bl, fadd(f.x, 0.0f), fadd(f.y, PF_GRAD_EPS));
-                const float gx = __fdiv_rn(fsub(ex, cur), PF_GRAD_EPS);
-                const float gy = __fdiv_rn(fsub(ey, cur), PF_GRAD_EPS);
-                f.x = fsub(f.x, fmul(PF_GRAD_STEP, gx));
-                f.y = fsub(f.y, fmul(PF_GRAD_STEP, gy));
-                a.flow[p] = f;
-            }
-            prev = f;
-            if (lane == 31 && bout != nullptr)
-                st_volatile_v4(bout + i, make_uint4(__float_as_uint(f.x), 1u, __float_as_uint(f.y), 1u));
-        }
-    }
-}
-
-size_t sweep_boundary_lines(int h, int w) {
-    const int nb = (h + 31) / 32;
-    return (size_t)(nb > 1 ? nb - 1 : 0) * (size_t)w;
-}
-
-void launch_sweep(const SweepArgs& a, int dir, cudaStream_t st) {
-    const int nb = (a.h + 31) / 32;
-    if (dir > 0) k_sweep<1><<<nb, 32, 0, st>>>(a);
-    else k_sweep<-1><<<nb, 32, 0, st>>>(a);
-}
-
-// ====================================================================================================
 // inter-level upsample: INTER_CUBIC on float2, then * (1/0.9)
 // ====================================================================================================
 __global__ void __launch_bounds__(256)

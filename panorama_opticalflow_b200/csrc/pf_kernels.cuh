@@ -32,17 +32,34 @@ void launch_blur15_cols(const float2* tmp, float2* dst, int h, int w,
 // ---- medianBlur(32FC2, 5) (CPU/PixFlow.hpp:325, :338) ------------------------------------------------
 void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st);
 
-// ---- Gauss-Seidel sweep as an exact anti-diagonal wavefront (CPU/PixFlow.hpp:315-337) ----------------
-struct SweepArgs {
-    const float* alpha0; const float* alpha1;
-    const float2* G0; const float2* G1; const float2* blurred;
-    float2* flow;
-    int h, w;
-    uint4* boundary;      // (nblocks-1) x w LL lines {fx, flag, fy, flag}, zero-initialised
+// ---- Gauss-Seidel sweeps as an exact anti-diagonal wavefront (CPU/PixFlow.hpp:315-337), pf_sweep.cu ------
+// Skewed (anti-diagonal-major) layout: element (x,y) at (x+y)*pitch + (posx ? x : y)
+struct Skew { int w, h, pitch, posx; };
+Skew make_skew(int w, int h);
+size_t skew_elems(const Skew& s);
+// row-major -> skewed copy of an interleaved gradient image
+void launch_skew_copy_f2(const float2* src, float2* dst, const Skew& s, cudaStream_t st);
+// per-pixel records for one sweep, in the wavefront-packed layout the sweep streams through shared memory:
+// a = {E(f0), r0.x, r0.y, -} (own-flow terms; {-inf, f0} where alpha <= 0.9), b = {I0x, I0y, blurred.x, blurred.y}.
+struct __align__(16) SweepRec { float4 a, b; };
+constexpr int SW_ROWS_PER_WARP_C = 4;     // logical rows per warp of the sweep kernel
+constexpr int SW_STREAM_DEPTH_C = 8;      // steps of cp.async lookahead on the record stream
+size_t sweep_rec_count(int h, int w);     // SweepRec elements a (h x w) level needs
+void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
+                       const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st);
+struct Sweep2Args {
+    const SweepRec* rec;                      // wavefront-packed records from launch_sweep_prep (same dir)
+    const float2* G1s;                        // skewed gradients of image 1
+    long long g1s_last;                       // index of the last element of G1s (prefetch clamp)
+    float2* flow;                             // row-major, updated in place where alpha > 0.9
+    Skew s;
+    uint4* boundary;      // LL lines {fx, flag, fy, flag}, zero-initialised (sweep2_boundary_lines of them)
     int* ticket;          // zero-initialised block ticket counter
+    int smem_ll;          // 1: warp-to-warp lines inside a CTA live in shared memory
 };
-size_t sweep_boundary_lines(int h, int w);   // number of uint4 lines a sweep of this size needs
-void launch_sweep(const SweepArgs& a, int dir, cudaStream_t st);
+bool sweep2_use_smem(int w);
+size_t sweep2_boundary_lines(int h, int w, bool smem_ll);
+void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st);
 
 // ---- inter-level upsample (CPU/PixFlow.hpp:123-124): INTER_CUBIC 32FC2 + "*= 1/0.9" --------------------
 void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int dh, int dw, cudaStream_t st);
@@ -62,5 +79,9 @@ void launch_combine(const uint8_t* imageL, size_t strideL, const uint8_t* imageR
                     const float2* flowLR, size_t strideLR, const float2* flowRL, size_t strideRL,
                     const float* blend, size_t strideB, int rows, int cols,
                     uint8_t* out, size_t strideOut, cudaStream_t st);
+
+// ---- exhaustive self-test of the branch-free exact division / square root (pf_selftest.cu) ---------------
+int selftest_exact_math(int wmin, int wmax, unsigned long long* out_mismatch_sqrt, unsigned long long* out_mismatch_eps,
+                        unsigned long long* out_mismatch_w, int* out_first_bad_w);
 
 }  // namespace pf

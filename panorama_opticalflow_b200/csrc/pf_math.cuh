@@ -133,3 +133,37 @@ __device__ __forceinline__ float error_function(const ErrCtx& c, int x, int y, f
 }
 
 }  // namespace pf
+
+// ---- branch-free exactly-rounded division and square root ------------------------------------------------
+// The sweep is latency-bound on one warp per scheduler, so the slow-path branches inside __fdiv_rn/__fsqrt_rn
+// cost more than their arithmetic.  These versions give the SAME correctly rounded results on a restricted
+// input range (checked exhaustively on the GPU by pf_selftest_exact_math / tests/test_gpu_exact_math.py);
+// callers track `bad` and redo the work with the IEEE intrinsics when an input leaves the range.
+namespace pf {
+
+// |x| in (2^-80, 2^80) or x == 0
+__device__ __forceinline__ bool in_safe_range(float x) {
+    const float a = fabsf(x);
+    return (a < 0x1p80f) && (a > 0x1p-80f || a == 0.0f);
+}
+
+// x / d for a loop-invariant divisor d with rd = RN(1/d): q = RN(x*rd), exact remainder by FMA, one correction
+// (Markstein).  FMA is used on purpose here: only the final, correctly rounded quotient matters.
+__device__ __forceinline__ float div_by_const(float x, float d, float rd) {
+    const float q = __fmul_rn(x, rd);
+    const float rem = __fmaf_rn(-q, d, x);
+    const float r = __fmaf_rn(rem, rd, q);
+    return x == 0.0f ? x : r;          // keeps the sign of a zero numerator (d > 0)
+}
+
+// sqrt(a) for a in (2^-80, 2^80) or a == 0: rsqrt seed, one Newton step with exact residual
+__device__ __forceinline__ float sqrt_exact_fast(float a) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    const float g = __fmul_rn(a, y), h = __fmul_rn(y, 0.5f);
+    const float r = __fmaf_rn(-g, g, a);
+    const float s = __fmaf_rn(r, h, g);
+    return a == 0.0f ? a : s;          // sqrt(+-0) = +-0
+}
+
+}  // namespace pf

@@ -1,0 +1,431 @@
+// pf_sweep.cu -- the Gauss-Seidel sweeps of PixFlow (CPU/PixFlow.hpp:315-337) as an exact anti-diagonal
+// wavefront, laid out for the B200 memory system.
+//
+// Why a wavefront is exact: the reference visits pixels in (reverse) raster order and updates the flow in
+// place; a pixel reads only its already-updated left/up (forward) or right/down (backward) neighbour from the
+// array being written.  Any order that respects those two dependencies gives bit-identical results, and the
+// anti-diagonal order is the one with the shortest critical path (w+h-1 steps).
+//
+// Data layout ("skewed", anti-diagonal-major): element (x,y) lives at (x+y)*pitch + pos, pos = x if w<=h else y.
+// All pixels a warp touches in one wavefront step sit on one anti-diagonal, i.e. in ONE contiguous run of memory:
+// every per-step load of the sweep is coalesced (1-2 cache lines) instead of one line per row.  The same holds
+// for the bilinear gathers of the I1 gradients as long as neighbouring rows have similar flow.
+//
+// Work split per pixel (i,j):
+//   * everything that depends only on the pixel's OWN old flow f0 -- E(f0), E(f0+dx), E(f0+dy) and the result
+//     r0 = f0 - step*grad(f0) that is kept when no neighbour proposal wins -- is hoisted into k_sweep_prep,
+//     a fully parallel kernel (record A = {E(f0), r0.x, r0.y}; inactive pixels get {-inf, f0});
+//   * the sweep kernel proper only evaluates the two neighbour candidates, speculatively and in parallel: eight
+//     lanes per row, lanes 0-2 take the left candidate (the row's own previous result) at offsets (0,0), (eps,0),
+//     (0,eps), lanes 3-5 the up candidate (previous result of the row above, one shuffle away) at the same three
+//     offsets -- ONE error evaluation per lane, so the dependent instruction chain of a step is one evaluation
+//     long.  Six shuffles hand every lane of the row all six errors; each lane then finishes both candidates'
+//     gradient steps and does the two compares.  Critical path per step: shuffle, bilinear gather, one error
+//     evaluation, shuffle, one division, two compares (measured: see profiles/).
+//   * the step body is branch-free: the IEEE divisions (by eps and by cols, both loop-invariant) and square roots
+//     use exactly-rounded branchless sequences (pf_math.cuh, verified exhaustively on the GPU); a warp-uniform
+//     vote redoes the step with the IEEE intrinsics in the rare case an operand leaves their validity range.
+//   * 4 rows per warp, 8 compute warps (32 rows) per CTA.  Warps hand the last row's results to the next warp
+//     through LL-style lines {fx, flag, fy, flag} (16-byte single-instruction stores, each 8-byte half
+//     self-validating, no fences, so L1 is never invalidated) in shared memory inside a CTA and in global memory
+//     between CTAs; a ninth "poller" warp per CTA spins on the upstream CTA's global lines and forwards them into
+//     shared memory, so no compute warp ever waits on an L2 round trip.  CTAs take their row block from an atomic
+//     ticket, so block b is always resident before block b+1 spins (no deadlock whatever the residency).
+#include "pf_kernels.cuh"
+#include "pf_math.cuh"
+
+namespace pf {
+
+// ---------------------------------------------------------------------------------------------------------
+// skewed layout helpers
+// ---------------------------------------------------------------------------------------------------------
+Skew make_skew(int w, int h) {
+    Skew s;
+    s.w = w; s.h = h;
+    s.posx = (w <= h) ? 1 : 0;
+    const int m = w <= h ? w : h;
+    s.pitch = (m + 7) & ~7;
+    return s;
+}
+size_t skew_elems(const Skew& s) { return (size_t)(s.w + s.h - 1) * (size_t)s.pitch; }
+
+__device__ __forceinline__ size_t skew_idx(const Skew& s, int x, int y) {
+    return (size_t)(x + y) * (size_t)s.pitch + (size_t)(s.posx ? x : y);
+}
+
+// Writes a 32x32 row-major tile held in shared memory (tile[ly*32+lx]) to the skewed array: one warp per
+// anti-diagonal of the tile, lanes along the diagonal -> contiguous global stores, conflict-free smem reads.
+template <class T>
+__device__ __forceinline__ void store_tile_skewed(const T* tile, T* __restrict__ out, const Skew& s, int x0, int y0,
+                                                  int warp, int nwarps, int lane) {
+    for (int ld = warp; ld < 63; ld += nwarps) {
+        const int lx = lane, ly = ld - lane;
+        if (ly >= 0 && ly < 32 && x0 + lx < s.w && y0 + ly < s.h)
+            out[skew_idx(s, x0 + lx, y0 + ly)] = tile[ly * 32 + lx];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_skew_copy_f2(const float2* __restrict__ src, float2* __restrict__ dst, Skew s) {
+    __shared__ float2 tile[32 * 32];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int lx = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ly = threadIdx.y + 8 * k;
+        const int x = x0 + lx, y = y0 + ly;
+        if (x < s.w && y < s.h) tile[ly * 32 + lx] = src[(size_t)y * s.w + x];
+    }
+    __syncthreads();
+    store_tile_skewed(tile, dst, s, x0, y0, threadIdx.y, 8, lx);
+}
+
+void launch_skew_copy_f2(const float2* src, float2* dst, const Skew& s, cudaStream_t st) {
+    dim3 b(32, 8), g((s.w + 31) / 32, (s.h + 31) / 32);
+    k_skew_copy_f2<<<g, b, 0, st>>>(src, dst, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sweep prep: everything that depends only on the pixel's own old flow (fully parallel).
+//
+// Output layout ("wavefront-packed"): the sweep gives 4 consecutive logical rows to a warp and at step s row g
+// of the warp handles logical column s-g.  Record (A,B) of that pixel is stored at
+//     rec[((wb * nsteps + s) * 4 + g)]            wb = logical row / 4, nsteps = w + 3
+// so everything one warp needs for one step is ONE 128-byte line and a warp consumes its lines strictly
+// sequentially -- which is what lets the sweep stage them through shared memory with cp.async many steps ahead.
+// ---------------------------------------------------------------------------------------------------------
+size_t sweep_rec_count(int h, int w) {
+    const size_t nblk = (size_t)(h + SW_ROWS_PER_WARP_C - 1) / SW_ROWS_PER_WARP_C;
+    return (nblk * (size_t)(w + SW_ROWS_PER_WARP_C - 1) + SW_STREAM_DEPTH_C + 1) * SW_ROWS_PER_WARP_C;
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256)
+k_sweep_prep(const float* __restrict__ alpha0, const float* __restrict__ alpha1, const float2* __restrict__ G0,
+             const float2* __restrict__ G1, const float2* __restrict__ blurred, const float2* __restrict__ flow,
+             SweepRec* __restrict__ rec, int h, int w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    ErrCtx c;
+    c.G1 = G1; c.w = w; c.h = h;
+    c.wm2 = fsub((float)w, 2.0f); c.hm2 = fsub((float)h, 2.0f); c.fw = (float)w;
+    const size_t p = (size_t)y * w + x;
+    const float2 f = flow[p];
+    const float2 g0 = G0[p];
+    const float2 bl = blurred[p];
+    float4 A = make_float4(__int_as_float(0xff800000), f.x, f.y, 0.0f);   // {-inf, f0}: never updated
+    if (alpha0[p] > PF_ALPHA_THRESHOLD && alpha1[p] > PF_ALPHA_THRESHOLD) {
+        const float e0 = error_function(c, x, y, g0, bl, f.x, f.y);
+        const float ex = error_function(c, x, y, g0, bl, fadd(f.x, PF_GRAD_EPS), fadd(f.y, 0.0f));
+        const float ey = error_function(c, x, y, g0, bl, fadd(f.x, 0.0f), fadd(f.y, PF_GRAD_EPS));
+        A.x = e0;
+        A.y = fsub(f.x, fmul(PF_GRAD_STEP, __fdiv_rn(fsub(ex, e0), PF_GRAD_EPS)));
+        A.z = fsub(f.y, fmul(PF_GRAD_STEP, __fdiv_rn(fsub(ey, e0), PF_GRAD_EPS)));
+    }
+    const int j = DIR > 0 ? y : h - 1 - y, i = DIR > 0 ? x : w - 1 - x;
+    const int wb = j / SW_ROWS_PER_WARP_C, g = j % SW_ROWS_PER_WARP_C;
+    const size_t idx = ((size_t)wb * (w + SW_ROWS_PER_WARP_C - 1) + (i + g)) * SW_ROWS_PER_WARP_C + g;
+    SweepRec r;
+    r.a = A;
+    r.b = make_float4(g0.x, g0.y, bl.x, bl.y);
+    rec[idx] = r;
+}
+
+void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
+                       const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st) {
+    dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
+    if (dir > 0) k_sweep_prep<1><<<g, b, 0, st>>>(alpha0, alpha1, G0, G1, blurred, flow, rec, h, w);
+    else k_sweep_prep<-1><<<g, b, 0, st>>>(alpha0, alpha1, G0, G1, blurred, flow, rec, h, w);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the wavefront sweep
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SW_P = 8;                        // lanes per row
+constexpr int SW_ROWS_PER_WARP = SW_ROWS_PER_WARP_C;    // 4
+static_assert(SW_ROWS_PER_WARP * SW_P == 32, "one warp = 4 rows x 8 lanes");
+constexpr int SW_STREAM_DEPTH = SW_STREAM_DEPTH_C;      // cp.async groups in flight per warp (steps of lookahead)
+constexpr int SW_STREAM_SLOTS = 16;                     // ring slots (power of two > depth)
+constexpr int SW_WARPS = 8;                    // compute warps per CTA (+ 1 poller warp)
+constexpr int SW_ROWS_PER_CTA = SW_ROWS_PER_WARP * SW_WARPS;
+constexpr int SW_THREADS = (SW_WARPS + 1) * 32;
+constexpr int SW_PREFETCH_GATHER = 4;   // steps ahead for the L1 warm-up of the gradient gather
+
+__device__ __forceinline__ uint4 ll_load_global(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void ll_store_global(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load_shared(const uint4* p) {
+    uint4 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void ll_store_shared(uint4* p, uint4 v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+struct SweepConst {
+    const float2* G1s;
+    uint4* touch;            // this lane's 16-byte scratch slot in shared memory (target of the L1 warm-up copies)
+    long long g1s_last, dstep;
+    int pitch, posx;
+    float wm2, hm2, fw, rcp_w, rcp_eps;
+};
+
+// errorFunction (CPU/PixFlow.hpp:427-456) for ONE flow candidate, gathering I1's gradients from the skewed layout.
+// SLOW = false: branch-free exact sequences, sets `bad` when an operand leaves their validity range.
+template <bool SLOW>
+__device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float yf, float2 g0, float2 bl, float fx, float fy, bool& bad) {
+    // getPixBilinear32FExtend, :407-425.  fmaxf/fminf == the std::max/std::min of the reference (NaN -> 0 included)
+    const float mx = fminf(fmaxf(fadd(xf, fx), 0.0f), k.wm2);
+    const float my = fminf(fmaxf(fadd(yf, fy), 0.0f), k.hm2);
+    const int x0 = __float2int_rz(mx), y0 = __float2int_rz(my);
+    const float xR = fsub(mx, (float)x0), yR = fsub(my, (float)y0);
+    const long long gi = (long long)(x0 + y0) * k.pitch + (k.posx ? x0 : y0);
+    const float2* p00 = k.G1s + gi;
+    const float2 f00 = __ldg(p00);
+    const float2 f10 = __ldg(p00 + k.pitch + k.posx);
+    const float2 f01 = __ldg(p00 + k.pitch + (1 - k.posx));
+    const float2 f11 = __ldg(p00 + 2 * k.pitch + 1);
+    {   // warm L1 with the anti-diagonal the gather reaches a few steps from now: an asynchronous 16-byte
+        // cp.async.ca into a scratch slot allocates the line in L1 and never blocks (its data is not used)
+        long long pi = gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
+        pi = pi < 0 ? 0 : (pi > k.g1s_last - 1 ? k.g1s_last - 1 : pi);
+        cp_async16(k.touch, k.G1s + (pi & ~1ll));
+    }
+    float g1x, g1y;
+    {
+        const float a2 = fsub(f10.x, f00.x), a3 = fsub(f01.x, f00.x);
+        const float a4 = fsub(fsub(fadd(f00.x, f11.x), f10.x), f01.x);
+        g1x = fadd(fadd(fadd(f00.x, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
+    }
+    {
+        const float a2 = fsub(f10.y, f00.y), a3 = fsub(f01.y, f00.y);
+        const float a4 = fsub(fsub(fadd(f00.y, f11.y), f10.y), f01.y);
+        g1y = fadd(fadd(fadd(f00.y, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
+    }
+    const float dX = fsub(bl.x, fx), dY = fsub(bl.y, fy);
+    const float ss = fadd(fmul(dX, dX), fmul(dY, dY));
+    const float ex = fsub(g0.x, g1x), ey = fsub(g0.y, g1y);
+    const float gs = fadd(fmul(ex, ex), fmul(ey, ey));
+    const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
+    float smooth, grad, ry, rx;
+    if (SLOW) {
+        smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
+        ry = __fdiv_rn(ty, k.fw); rx = __fdiv_rn(tx, k.fw);
+    } else {
+        smooth = sqrt_exact_fast(ss); grad = sqrt_exact_fast(gs);
+        ry = div_by_const(ty, k.fw, k.rcp_w); rx = div_by_const(tx, k.fw, k.rcp_w);
+        bad = bad || !(in_safe_range(ss) && in_safe_range(gs) && in_safe_range(ty) && in_safe_range(tx));
+    }
+    float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
+    err = fadd(err, ry);
+    err = fadd(err, rx);
+    return err;
+}
+
+// From one error per lane to the pixel's result: six shuffles give every lane of the row the errors of both
+// candidates at the three probe offsets; finish both gradient steps (CPU/PixFlow.hpp:321, :364-386) and select in the
+// reference's order (:318-320: left proposal first, then up, strict <).
+template <bool SLOW>
+__device__ __forceinline__ float2 finish_pixel(const SweepConst& k, float v, int gbase, float2 left, float2 up,
+                                               bool leftValid, bool upValid, float4 A, bool& bad) {
+    const unsigned full = 0xffffffffu;
+    float eL = __shfl_sync(full, v, gbase + 0);
+    const float eLx = __shfl_sync(full, v, gbase + 1);
+    const float eLy = __shfl_sync(full, v, gbase + 2);
+    float eU = __shfl_sync(full, v, gbase + 3);
+    const float eUx = __shfl_sync(full, v, gbase + 4);
+    const float eUy = __shfl_sync(full, v, gbase + 5);
+    const float dLx = fsub(eLx, eL), dLy = fsub(eLy, eL), dUx = fsub(eUx, eU), dUy = fsub(eUy, eU);
+    float qLx, qLy, qUx, qUy;
+    if (SLOW) {
+        qLx = __fdiv_rn(dLx, PF_GRAD_EPS); qLy = __fdiv_rn(dLy, PF_GRAD_EPS);
+        qUx = __fdiv_rn(dUx, PF_GRAD_EPS); qUy = __fdiv_rn(dUy, PF_GRAD_EPS);
+    } else {
+        qLx = div_by_const(dLx, PF_GRAD_EPS, k.rcp_eps); qLy = div_by_const(dLy, PF_GRAD_EPS, k.rcp_eps);
+        qUx = div_by_const(dUx, PF_GRAD_EPS, k.rcp_eps); qUy = div_by_const(dUy, PF_GRAD_EPS, k.rcp_eps);
+        bad = bad || !(in_safe_range(dLx) && in_safe_range(dLy) && in_safe_range(dUx) && in_safe_range(dUy));
+    }
+    const float2 rL = make_float2(fsub(left.x, fmul(PF_GRAD_STEP, qLx)), fsub(left.y, fmul(PF_GRAD_STEP, qLy)));
+    const float2 rU = make_float2(fsub(up.x, fmul(PF_GRAD_STEP, qUx)), fsub(up.y, fmul(PF_GRAD_STEP, qUy)));
+    const float POS_INF = __int_as_float(0x7f800000);
+    eL = leftValid ? eL : POS_INF;
+    eU = upValid ? eU : POS_INF;
+    float cur = A.x;
+    float2 out = make_float2(A.y, A.z);
+    if (eL < cur) { out = rL; cur = eL; }
+    if (eU < cur) { out = rU; cur = eU; }
+    return out;
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(SW_THREADS)
+k_sweep3(Sweep2Args a) {
+    // dynamic shared memory: [SW_WARPS x w] LL lines when a.smem_ll ([0] inbound via the poller, [k] from warp k-1)
+    extern __shared__ uint4 s_ll[];
+    __shared__ int s_b;
+    __shared__ __align__(128) SweepRec s_ring[SW_WARPS][SW_STREAM_SLOTS][SW_ROWS_PER_WARP];   // 16 KB
+    __shared__ uint4 s_touch[SW_WARPS][32];
+    const unsigned full = 0xffffffffu;
+    const int w = a.s.w, h = a.s.h;
+    if (threadIdx.x == 0) s_b = atomicAdd(a.ticket, 1);
+    if (a.smem_ll)
+        for (int i = threadIdx.x; i < SW_WARPS * w; i += SW_THREADS) s_ll[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const int b = s_b;
+    const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (wi == SW_WARPS) {
+        // ---- poller warp: forward the upstream CTA's global LL lines into shared memory as they become valid ----
+        if (!a.smem_ll || b == 0) return;
+        const uint4* src = a.boundary + (size_t)(b - 1) * w;
+        for (int base = 0; base < w; base += 32) {
+            const int col = base + lane;
+            bool done = col >= w;
+            while (!__all_sync(full, done)) {
+                if (!done) {
+                    const uint4 v = ll_load_global(src + col);
+                    if (v.y == 1u && v.w == 1u) { ll_store_shared(s_ll + col, v); done = true; }
+                }
+            }
+        }
+        return;
+    }
+
+    const int g = lane >> 3, kk = lane & 7, gbase = lane & ~7;
+    const int jw = b * SW_ROWS_PER_CTA + wi * SW_ROWS_PER_WARP;    // first logical row of this warp
+    if (jw >= h) return;
+    const int j = jw + g;
+    const bool rowValid = j < h;
+    const int y = DIR > 0 ? j : h - 1 - j;
+
+    // LL lines in (from the warp above) and out (to the warp below)
+    const uint4* ll_in = nullptr; bool in_sh = false;
+    if (jw > 0) {
+        if (a.smem_ll) { ll_in = s_ll + (size_t)wi * w; in_sh = true; }
+        else ll_in = a.boundary + (size_t)(b * SW_WARPS + wi - 1) * w;
+    }
+    uint4* ll_out = nullptr; bool out_sh = false;
+    if (jw + SW_ROWS_PER_WARP < h) {
+        if (wi < SW_WARPS - 1 && a.smem_ll) { ll_out = s_ll + (size_t)(wi + 1) * w; out_sh = true; }
+        else ll_out = a.boundary + (size_t)(a.smem_ll ? b : b * SW_WARPS + wi) * w;
+    }
+    const bool has_in = ll_in != nullptr;
+
+    SweepConst k;
+    k.G1s = a.G1s; k.g1s_last = a.g1s_last;
+    k.touch = &s_touch[wi][lane];
+    k.pitch = a.s.pitch; k.posx = a.s.posx;
+    k.dstep = (long long)DIR * (k.pitch + k.posx);
+    k.wm2 = fsub((float)w, 2.0f); k.hm2 = fsub((float)h, 2.0f); k.fw = (float)w;
+    k.rcp_w = __frcp_rn(k.fw); k.rcp_eps = __frcp_rn(PF_GRAD_EPS);
+    const float NEG_INF = __int_as_float(0xff800000);
+    // this lane's probe: lanes 0-2 left candidate, 3-5 up candidate (6, 7 duplicate 3, 4), offsets (0,0) (eps,0) (0,eps)
+    const bool candUp = kk >= 3;
+    const int probe = kk % 3;
+    const float offx = probe == 1 ? PF_GRAD_EPS : 0.0f, offy = probe == 2 ? PF_GRAD_EPS : 0.0f;
+    const float yf = (float)y;
+
+    // ---- record stream: one 128-byte line per step, staged through a shared-memory ring with cp.async ----
+    const int nsteps = w + SW_ROWS_PER_WARP - 1;
+    const uint4* stream = reinterpret_cast<const uint4*>(a.rec + (size_t)(jw / SW_ROWS_PER_WARP) * nsteps * SW_ROWS_PER_WARP);
+    uint4* ring = reinterpret_cast<uint4*>(&s_ring[wi][0][0]);          // 8 x uint4 per slot
+    for (int t = 0; t < SW_STREAM_DEPTH; ++t) {                         // prologue: steps 0 .. depth-1
+        if (kk == lane) cp_async16(ring + (t & (SW_STREAM_SLOTS - 1)) * 8 + lane, stream + (size_t)t * 8 + lane);   // lanes 0-7
+        cp_async_commit();
+    }
+
+    float2 res = make_float2(0.0f, 0.0f);
+    uint4 ln = make_uint4(0u, 0u, 0u, 0u);
+    if (has_in) ln = in_sh ? ll_load_shared(ll_in) : ll_load_global(ll_in);
+
+    for (int s = 0; s < nsteps; ++s) {
+        const int i = s - g;                      // logical column of this row at this step
+        // ---- records: issue the line of step s+depth, wait for the line of step s ----
+        if (kk == lane) cp_async16(ring + ((s + SW_STREAM_DEPTH) & (SW_STREAM_SLOTS - 1)) * 8 + lane, stream + (size_t)(s + SW_STREAM_DEPTH) * 8 + lane);
+        cp_async_commit();
+        cp_async_wait<SW_STREAM_DEPTH>();
+        __syncwarp();
+        const uint4* slot = ring + (s & (SW_STREAM_SLOTS - 1)) * 8 + g * 2;
+        const float4 A = *reinterpret_cast<const float4*>(slot);
+        const float4 B = *reinterpret_cast<const float4*>(slot + 1);
+        // ---- up neighbour: previous result of the row above (shuffle; first row of the warp: LL line) ----
+        float2 up;
+        up.x = __shfl_up_sync(full, res.x, SW_P);
+        up.y = __shfl_up_sync(full, res.y, SW_P);
+        if (has_in && s < w) {                    // warp-uniform: every lane reads the same line
+            uint4 v = ln;
+            while (v.y != 1u || v.w != 1u) v = in_sh ? ll_load_shared(ll_in + s) : ll_load_global(ll_in + s);
+            if (s + 1 < w) ln = in_sh ? ll_load_shared(ll_in + s + 1) : ll_load_global(ll_in + s + 1);
+            if (g == 0) { up.x = __uint_as_float(v.x); up.y = __uint_as_float(v.z); }
+        }
+        const bool valid = rowValid && i >= 0 && i < w;
+        const bool active = valid && A.x > NEG_INF;
+        const int x = DIR > 0 ? i : w - 1 - i;
+        float2 out = make_float2(A.y, A.z);
+        if (__any_sync(full, active)) {           // warp-uniform: skip fully inactive stretches
+            const float2 cand = candUp ? up : res;
+            const float2 g0 = make_float2(B.x, B.y), bl = make_float2(B.z, B.w);
+            const float fx = fadd(cand.x, offx), fy = fadd(cand.y, offy);
+            bool bad = false;
+            float v = eval_err<false>(k, (float)x, yf, g0, bl, fx, fy, bad);
+            out = finish_pixel<false>(k, v, gbase, res, up, i > 0, j > 0, A, bad);
+            if (__any_sync(full, bad && active)) {   // rare: an operand left the branch-free range -> IEEE intrinsics
+                bool dummy = false;
+                v = eval_err<true>(k, (float)x, yf, g0, bl, fx, fy, dummy);
+                out = finish_pixel<true>(k, v, gbase, res, up, i > 0, j > 0, A, dummy);
+            }
+        }
+        if (valid) {
+            res = out;
+            if (kk == 0) {
+                if (active) a.flow[(size_t)y * w + x] = out;    // inactive pixels keep their flow
+                if (g == SW_ROWS_PER_WARP - 1 && ll_out != nullptr) {
+                    const uint4 v = make_uint4(__float_as_uint(out.x), 1u, __float_as_uint(out.y), 1u);
+                    if (out_sh) ll_store_shared(ll_out + i, v); else ll_store_global(ll_out + i, v);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+size_t sweep2_boundary_lines(int h, int w, bool smem_ll) {
+    const int ncta = (h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
+    const int nwarp = ncta * SW_WARPS;
+    const int n = smem_ll ? ncta - 1 : nwarp - 1;
+    return (size_t)(n > 0 ? n : 0) * (size_t)w + 1;
+}
+
+bool sweep2_use_smem(int w) { return (size_t)SW_WARPS * w * sizeof(uint4) <= 180 * 1024; }
+
+void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {   // opt in to > 48 KB of dynamic shared memory, once per device
+        cudaFuncSetAttribute(k_sweep3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_sweep3<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set[dev] = true;
+    }
+    const int ncta = (a.s.h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
+    const size_t smem = a.smem_ll ? (size_t)SW_WARPS * a.s.w * sizeof(uint4) : 0;
+    if (dir > 0) k_sweep3<1><<<ncta, SW_THREADS, smem, st>>>(a);
+    else k_sweep3<-1><<<ncta, SW_THREADS, smem, st>>>(a);
+}
+
+}  // namespace pf
