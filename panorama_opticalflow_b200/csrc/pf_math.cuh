@@ -141,11 +141,15 @@ __device__ __forceinline__ float error_function(const ErrCtx& c, int x, int y, f
 // callers track `bad` and redo the work with the IEEE intrinsics when an input leaves the range.
 namespace pf {
 
-// |x| in (2^-80, 2^80) or x == 0
-__device__ __forceinline__ bool in_safe_range(float x) {
-    const float a = fabsf(x);
-    return (a < 0x1p80f) && (a > 0x1p-80f || a == 0.0f);
-}
+// Validity ranges of the branch-free sequences below (checked exhaustively by pf_selftest_exact_math):
+//   sqrt_exact_fast(a):     a == 0 or 2^-60 <= a < 2^126
+//   div_by_const(x, d, rd): x == 0 or 2^-60 <= |x| < 2^100, for d = 0.001f and every integer d in [24, 16384]
+#define PF_TINY_BITS 0x21800000u      /* float bits of 2^-60 */
+__device__ __forceinline__ bool in_sqrt_range(float a) { return a == 0.0f || (a >= 0x1p-60f && a < 0x1p126f); }
+__device__ __forceinline__ bool in_div_range(float x) { const float a = fabsf(x); return a == 0.0f || (a >= 0x1p-60f && a < 0x1p100f); }
+// key of a non-negative operand for the "tiny but non-zero" test: min over keys < PF_TINY_BITS-1  <=>  some
+// operand lies in (0, 2^-60).  (0 maps to 0xffffffff.)
+__device__ __forceinline__ unsigned tiny_key(float x_nonneg) { return __float_as_uint(x_nonneg) - 1u; }
 
 // x / d for a loop-invariant divisor d with rd = RN(1/d): q = RN(x*rd), exact remainder by FMA, one correction
 // (Markstein).  FMA is used on purpose here: only the final, correctly rounded quotient matters.

@@ -11,7 +11,7 @@ __global__ void k_selftest_sqrt(unsigned long long* mismatches) {
     for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n;
          v += (unsigned long long)gridDim.x * blockDim.x) {
         const float a = __uint_as_float((unsigned)v);
-        if (!(a >= 0.0f) || !in_safe_range(a)) continue;
+        if (!(a >= 0.0f) || !in_sqrt_range(a)) continue;
         const float want = __fsqrt_rn(a), got = sqrt_exact_fast(a);
         if (__float_as_uint(want) != __float_as_uint(got)) ++bad;
     }
@@ -25,7 +25,7 @@ __global__ void k_selftest_div(float d, float rd, unsigned long long* mismatches
     for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n;
          v += (unsigned long long)gridDim.x * blockDim.x) {
         const float x = __uint_as_float((unsigned)v);
-        if (!in_safe_range(x)) continue;
+        if (!in_div_range(x)) continue;
         const float want = __fdiv_rn(x, d), got = div_by_const(x, d, rd);
         if (__float_as_uint(want) != __float_as_uint(got)) ++bad;
     }

@@ -29,8 +29,12 @@
 //     through LL-style lines {fx, flag, fy, flag} (16-byte single-instruction stores, each 8-byte half
 //     self-validating, no fences, so L1 is never invalidated) in shared memory inside a CTA and in global memory
 //     between CTAs; a ninth "poller" warp per CTA spins on the upstream CTA's global lines and forwards them into
-//     shared memory, so no compute warp ever waits on an L2 round trip.  CTAs take their row block from an atomic
-//     ticket, so block b is always resident before block b+1 spins (no deadlock whatever the residency).
+//     shared memory, so no compute warp ever waits on an L2 round trip.  The shared-memory lines are 64-entry rings
+//     (flag = lap number, back-pressure through a progress counter), so a CTA needs < 32 KB of shared memory and
+//     several sweeps (both directions, several pairs) are co-resident on an SM -- the step is latency-bound on
+//     one warp, so throughput comes from interleaving independent wavefronts on the same schedulers.  CTAs take
+//     their row block from an atomic ticket, so block b is always resident before block b+1 spins (no deadlock
+//     whatever the residency).
 #include "pf_kernels.cuh"
 #include "pf_math.cuh"
 
@@ -150,7 +154,9 @@ constexpr int SW_STREAM_SLOTS = 16;                     // ring slots (power of 
 constexpr int SW_WARPS = 8;                    // compute warps per CTA (+ 1 poller warp)
 constexpr int SW_ROWS_PER_CTA = SW_ROWS_PER_WARP * SW_WARPS;
 constexpr int SW_THREADS = (SW_WARPS + 1) * 32;
-constexpr int SW_PREFETCH_GATHER = 4;   // steps ahead for the L1 warm-up of the gradient gather
+constexpr int SW_PREFETCH_GATHER = 4;          // steps ahead for the L1 warm-up of the gradient gather
+constexpr int SW_LL_RING = 64;                 // entries of a shared-memory LL ring (power of two)
+constexpr int SW_PROGRESS_EVERY = 8;           // consumer publishes its progress every 8 columns
 
 __device__ __forceinline__ uint4 ll_load_global(const uint4* p) {
     uint4 v;
@@ -160,51 +166,58 @@ __device__ __forceinline__ uint4 ll_load_global(const uint4* p) {
 __device__ __forceinline__ void ll_store_global(uint4* p, uint4 v) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ uint4 ll_load_shared(const uint4* p) {
+__device__ __forceinline__ uint4 ll_load_shared(unsigned saddr) {
     uint4 v;
-    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ void ll_store_shared(uint4* p, uint4 v) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void ll_store_shared(unsigned saddr, uint4 v) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+__device__ __forceinline__ int ld_volatile_shared_s32(unsigned saddr) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared_s32(unsigned saddr, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 struct SweepConst {
     const float2* G1s;
-    uint4* touch;            // this lane's 16-byte scratch slot in shared memory (target of the L1 warm-up copies)
-    long long g1s_last, dstep;
-    int pitch, posx;
+    unsigned touch;          // this lane's 16-byte scratch slot in shared memory (target of the L1 warm-up copies)
+    int g1s_last, dstep, pitch;
     float wm2, hm2, fw, rcp_w, rcp_eps;
 };
 
 // errorFunction (CPU/PixFlow.hpp:427-456) for ONE flow candidate, gathering I1's gradients from the skewed layout.
-// SLOW = false: branch-free exact sequences, sets `bad` when an operand leaves their validity range.
-template <bool SLOW>
-__device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float yf, float2 g0, float2 bl, float fx, float fy, bool& bad) {
+// SLOW = false: branch-free exact sequences; `tiny` collects the keys of their operands (see tiny_key).
+template <int POSX, bool SLOW>
+__device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float yf, float2 g0, float2 bl, float fx, float fy, unsigned& tiny) {
     // getPixBilinear32FExtend, :407-425.  fmaxf/fminf == the std::max/std::min of the reference (NaN -> 0 included)
     const float mx = fminf(fmaxf(fadd(xf, fx), 0.0f), k.wm2);
     const float my = fminf(fmaxf(fadd(yf, fy), 0.0f), k.hm2);
     const int x0 = __float2int_rz(mx), y0 = __float2int_rz(my);
-    const float xR = fsub(mx, (float)x0), yR = fsub(my, (float)y0);
-    const long long gi = (long long)(x0 + y0) * k.pitch + (k.posx ? x0 : y0);
+    const float xR = fsub(mx, truncf(mx)), yR = fsub(my, truncf(my));
+    const int gi = (x0 + y0) * k.pitch + (POSX ? x0 : y0);
     const float2* p00 = k.G1s + gi;
+    const float2* p1 = p00 + k.pitch;            // anti-diagonal +1: (x0,y0+1) and (x0+1,y0) are adjacent
+    const float2* p2 = p1 + k.pitch;             // anti-diagonal +2
     const float2 f00 = __ldg(p00);
-    const float2 f10 = __ldg(p00 + k.pitch + k.posx);
-    const float2 f01 = __ldg(p00 + k.pitch + (1 - k.posx));
-    const float2 f11 = __ldg(p00 + 2 * k.pitch + 1);
+    const float2 f10 = __ldg(p1 + (POSX ? 1 : 0));
+    const float2 f01 = __ldg(p1 + (POSX ? 0 : 1));
+    const float2 f11 = __ldg(p2 + 1);
     {   // warm L1 with the anti-diagonal the gather reaches a few steps from now: an asynchronous 16-byte
         // cp.async.ca into a scratch slot allocates the line in L1 and never blocks (its data is not used)
-        long long pi = gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
-        pi = pi < 0 ? 0 : (pi > k.g1s_last - 1 ? k.g1s_last - 1 : pi);
-        cp_async16(k.touch, k.G1s + (pi & ~1ll));
+        int pi = gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
+        pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
+        cp_async16(k.touch, k.G1s + pi);
     }
     float g1x, g1y;
     {
@@ -229,7 +242,7 @@ __device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float y
     } else {
         smooth = sqrt_exact_fast(ss); grad = sqrt_exact_fast(gs);
         ry = div_by_const(ty, k.fw, k.rcp_w); rx = div_by_const(tx, k.fw, k.rcp_w);
-        bad = bad || !(in_safe_range(ss) && in_safe_range(gs) && in_safe_range(ty) && in_safe_range(tx));
+        tiny = min(min(tiny_key(ss), tiny_key(gs)), min(tiny_key(ty), tiny_key(tx)));
     }
     float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
     err = fadd(err, ry);
@@ -242,7 +255,7 @@ __device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float y
 // reference's order (:318-320: left proposal first, then up, strict <).
 template <bool SLOW>
 __device__ __forceinline__ float2 finish_pixel(const SweepConst& k, float v, int gbase, float2 left, float2 up,
-                                               bool leftValid, bool upValid, float4 A, bool& bad) {
+                                               bool leftValid, bool upValid, float4 A, unsigned& tiny) {
     const unsigned full = 0xffffffffu;
     float eL = __shfl_sync(full, v, gbase + 0);
     const float eLx = __shfl_sync(full, v, gbase + 1);
@@ -258,7 +271,7 @@ __device__ __forceinline__ float2 finish_pixel(const SweepConst& k, float v, int
     } else {
         qLx = div_by_const(dLx, PF_GRAD_EPS, k.rcp_eps); qLy = div_by_const(dLy, PF_GRAD_EPS, k.rcp_eps);
         qUx = div_by_const(dUx, PF_GRAD_EPS, k.rcp_eps); qUy = div_by_const(dUy, PF_GRAD_EPS, k.rcp_eps);
-        bad = bad || !(in_safe_range(dLx) && in_safe_range(dLy) && in_safe_range(dUx) && in_safe_range(dUy));
+        tiny = min(min(tiny_key(fabsf(dLx)), tiny_key(fabsf(dLy))), min(tiny_key(fabsf(dUx)), tiny_key(fabsf(dUy))));
     }
     const float2 rL = make_float2(fsub(left.x, fmul(PF_GRAD_STEP, qLx)), fsub(left.y, fmul(PF_GRAD_STEP, qLy)));
     const float2 rU = make_float2(fsub(up.x, fmul(PF_GRAD_STEP, qUx)), fsub(up.y, fmul(PF_GRAD_STEP, qUy)));
@@ -272,160 +285,167 @@ __device__ __forceinline__ float2 finish_pixel(const SweepConst& k, float v, int
     return out;
 }
 
-template <int DIR>
-__global__ void __launch_bounds__(SW_THREADS)
-k_sweep3(Sweep2Args a) {
-    // dynamic shared memory: [SW_WARPS x w] LL lines when a.smem_ll ([0] inbound via the poller, [k] from warp k-1)
-    extern __shared__ uint4 s_ll[];
+template <int DIR, int POSX>
+__global__ void __launch_bounds__(SW_THREADS, 3)
+k_sweep5(Sweep2Args a) {
     __shared__ int s_b;
+    __shared__ int s_progress[SW_WARPS];                                  // columns consumed from ring k
+    __shared__ __align__(16) uint4 s_llring[SW_WARPS][SW_LL_RING];        // [0] inbound via the poller, [k] from warp k-1
     __shared__ __align__(128) SweepRec s_ring[SW_WARPS][SW_STREAM_SLOTS][SW_ROWS_PER_WARP];   // 16 KB
     __shared__ uint4 s_touch[SW_WARPS][32];
     const unsigned full = 0xffffffffu;
-    const int w = a.s.w, h = a.s.h;
+    int w = a.s.w, h = a.s.h;
     if (threadIdx.x == 0) s_b = atomicAdd(a.ticket, 1);
-    if (a.smem_ll)
-        for (int i = threadIdx.x; i < SW_WARPS * w; i += SW_THREADS) s_ll[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < SW_WARPS * SW_LL_RING; i += SW_THREADS) (&s_llring[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < SW_WARPS) s_progress[threadIdx.x] = 0;
     __syncthreads();
     const int b = s_b;
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (wi == SW_WARPS) {
-        // ---- poller warp: forward the upstream CTA's global LL lines into shared memory as they become valid ----
-        if (!a.smem_ll || b == 0) return;
+        // ---- poller warp: forward the upstream CTA's global LL lines into ring 0 as they become valid ----
+        if (b == 0) return;
         const uint4* src = a.boundary + (size_t)(b - 1) * w;
+        const unsigned prog = smem_u32(&s_progress[0]);
+        const unsigned ring0 = smem_u32(&s_llring[0][0]);
         for (int base = 0; base < w; base += 32) {
+            while (base + 32 > ld_volatile_shared_s32(prog) + SW_LL_RING) { }    // back-pressure: batch must fit
             const int col = base + lane;
             bool done = col >= w;
             while (!__all_sync(full, done)) {
                 if (!done) {
                     const uint4 v = ll_load_global(src + col);
-                    if (v.y == 1u && v.w == 1u) { ll_store_shared(s_ll + col, v); done = true; }
+                    if (v.y == 1u && v.w == 1u) {
+                        const unsigned e = (unsigned)(col / SW_LL_RING) + 1u;
+                        ll_store_shared(ring0 + (col & (SW_LL_RING - 1)) * 16, make_uint4(v.x, e, v.z, e));
+                        done = true;
+                    }
                 }
             }
         }
         return;
     }
 
-    const int g = lane >> 3, kk = lane & 7, gbase = lane & ~7;
+    const int g = lane >> 3, kk = lane & 7, gbase = lane & 24;
     const int jw = b * SW_ROWS_PER_CTA + wi * SW_ROWS_PER_WARP;    // first logical row of this warp
     if (jw >= h) return;
     const int j = jw + g;
     const bool rowValid = j < h;
     const int y = DIR > 0 ? j : h - 1 - j;
-
-    // LL lines in (from the warp above) and out (to the warp below)
-    const uint4* ll_in = nullptr; bool in_sh = false;
-    if (jw > 0) {
-        if (a.smem_ll) { ll_in = s_ll + (size_t)wi * w; in_sh = true; }
-        else ll_in = a.boundary + (size_t)(b * SW_WARPS + wi - 1) * w;
-    }
-    uint4* ll_out = nullptr; bool out_sh = false;
-    if (jw + SW_ROWS_PER_WARP < h) {
-        if (wi < SW_WARPS - 1 && a.smem_ll) { ll_out = s_ll + (size_t)(wi + 1) * w; out_sh = true; }
-        else ll_out = a.boundary + (size_t)(a.smem_ll ? b : b * SW_WARPS + wi) * w;
-    }
-    const bool has_in = ll_in != nullptr;
+    const bool has_in = jw > 0;                                    // warp-uniform
+    const bool has_out = jw + SW_ROWS_PER_WARP < h;                // warp-uniform
+    const bool out_global = wi == SW_WARPS - 1;
+    const unsigned rin = smem_u32(&s_llring[wi][0]);
+    const unsigned rout = smem_u32(&s_llring[(wi + 1) & (SW_WARPS - 1)][0]);
+    const unsigned prog_in = smem_u32(&s_progress[wi]);
+    const unsigned prog_out = smem_u32(&s_progress[(wi + 1) & (SW_WARPS - 1)]);
+    uint4* gout = a.boundary + (size_t)b * w;
+    int out_limit = SW_LL_RING;                                    // columns < out_limit fit in the out ring unchecked
 
     SweepConst k;
-    k.G1s = a.G1s; k.g1s_last = a.g1s_last;
-    k.touch = &s_touch[wi][lane];
-    k.pitch = a.s.pitch; k.posx = a.s.posx;
-    k.dstep = (long long)DIR * (k.pitch + k.posx);
+    k.G1s = a.G1s; k.g1s_last = (int)a.g1s_last;
+    k.touch = smem_u32(&s_touch[wi][lane]);
+    k.pitch = a.s.pitch;
+    k.dstep = DIR * (k.pitch + POSX);
     k.wm2 = fsub((float)w, 2.0f); k.hm2 = fsub((float)h, 2.0f); k.fw = (float)w;
     k.rcp_w = __frcp_rn(k.fw); k.rcp_eps = __frcp_rn(PF_GRAD_EPS);
+    asm volatile("" : "+r"(w), "+r"(k.pitch), "+r"(k.dstep), "+r"(k.g1s_last));     // keep loop invariants in registers
+    asm volatile("" : "+f"(k.wm2), "+f"(k.hm2), "+f"(k.fw), "+f"(k.rcp_w), "+f"(k.rcp_eps));
     const float NEG_INF = __int_as_float(0xff800000);
     // this lane's probe: lanes 0-2 left candidate, 3-5 up candidate (6, 7 duplicate 3, 4), offsets (0,0) (eps,0) (0,eps)
     const bool candUp = kk >= 3;
     const int probe = kk % 3;
     const float offx = probe == 1 ? PF_GRAD_EPS : 0.0f, offy = probe == 2 ? PF_GRAD_EPS : 0.0f;
     const float yf = (float)y;
+    float xf = (float)(DIR > 0 ? -g : w - 1 + g);                  // float(x) of step 0, then +-1 per step (exact)
+    float2* flow_row = a.flow + (size_t)y * w;
 
     // ---- record stream: one 128-byte line per step, staged through a shared-memory ring with cp.async ----
     const int nsteps = w + SW_ROWS_PER_WARP - 1;
-    const uint4* stream = reinterpret_cast<const uint4*>(a.rec + (size_t)(jw / SW_ROWS_PER_WARP) * nsteps * SW_ROWS_PER_WARP);
-    uint4* ring = reinterpret_cast<uint4*>(&s_ring[wi][0][0]);          // 8 x uint4 per slot
-    for (int t = 0; t < SW_STREAM_DEPTH; ++t) {                         // prologue: steps 0 .. depth-1
-        if (kk == lane) cp_async16(ring + (t & (SW_STREAM_SLOTS - 1)) * 8 + lane, stream + (size_t)t * 8 + lane);   // lanes 0-7
+    const uint4* stream = reinterpret_cast<const uint4*>(a.rec + (size_t)(jw / SW_ROWS_PER_WARP) * nsteps * SW_ROWS_PER_WARP) + lane;
+    const unsigned ring = smem_u32(&s_ring[wi][0][0]);             // 128 bytes per slot
+    for (int t = 0; t < SW_STREAM_DEPTH; ++t) {                    // prologue: steps 0 .. depth-1
+        if (lane < 8) cp_async16(ring + (t & (SW_STREAM_SLOTS - 1)) * 128 + lane * 16, stream + (size_t)t * 8);
         cp_async_commit();
     }
+    const uint4* s_slot0 = reinterpret_cast<const uint4*>(&s_ring[wi][0][g]);
 
     float2 res = make_float2(0.0f, 0.0f);
     uint4 ln = make_uint4(0u, 0u, 0u, 0u);
-    if (has_in) ln = in_sh ? ll_load_shared(ll_in) : ll_load_global(ll_in);
+    if (has_in) ln = ll_load_shared(rin);
 
     for (int s = 0; s < nsteps; ++s) {
         const int i = s - g;                      // logical column of this row at this step
         // ---- records: issue the line of step s+depth, wait for the line of step s ----
-        if (kk == lane) cp_async16(ring + ((s + SW_STREAM_DEPTH) & (SW_STREAM_SLOTS - 1)) * 8 + lane, stream + (size_t)(s + SW_STREAM_DEPTH) * 8 + lane);
+        if (lane < 8) cp_async16(ring + ((s + SW_STREAM_DEPTH) & (SW_STREAM_SLOTS - 1)) * 128 + lane * 16, stream + (size_t)(s + SW_STREAM_DEPTH) * 8);
         cp_async_commit();
         cp_async_wait<SW_STREAM_DEPTH>();
         __syncwarp();
-        const uint4* slot = ring + (s & (SW_STREAM_SLOTS - 1)) * 8 + g * 2;
+        const uint4* slot = s_slot0 + (s & (SW_STREAM_SLOTS - 1)) * 8;
         const float4 A = *reinterpret_cast<const float4*>(slot);
         const float4 B = *reinterpret_cast<const float4*>(slot + 1);
-        // ---- up neighbour: previous result of the row above (shuffle; first row of the warp: LL line) ----
+        // ---- up neighbour: previous result of the row above (shuffle; first row of the warp: LL ring) ----
         float2 up;
         up.x = __shfl_up_sync(full, res.x, SW_P);
         up.y = __shfl_up_sync(full, res.y, SW_P);
-        if (has_in && s < w) {                    // warp-uniform: every lane reads the same line
+        if (has_in && s < w) {                    // warp-uniform: every lane reads the same ring entry
+            const unsigned e = (unsigned)(s / SW_LL_RING) + 1u;
             uint4 v = ln;
-            while (v.y != 1u || v.w != 1u) v = in_sh ? ll_load_shared(ll_in + s) : ll_load_global(ll_in + s);
-            if (s + 1 < w) ln = in_sh ? ll_load_shared(ll_in + s + 1) : ll_load_global(ll_in + s + 1);
+            while (v.y != e || v.w != e) v = ll_load_shared(rin + (s & (SW_LL_RING - 1)) * 16);
+            ln = ll_load_shared(rin + ((s + 1) & (SW_LL_RING - 1)) * 16);
+            if ((s & (SW_PROGRESS_EVERY - 1)) == SW_PROGRESS_EVERY - 1 && lane == 0) st_volatile_shared_s32(prog_in, s + 1);
             if (g == 0) { up.x = __uint_as_float(v.x); up.y = __uint_as_float(v.z); }
         }
-        const bool valid = rowValid && i >= 0 && i < w;
+        const bool valid = rowValid && (unsigned)i < (unsigned)w;
         const bool active = valid && A.x > NEG_INF;
-        const int x = DIR > 0 ? i : w - 1 - i;
         float2 out = make_float2(A.y, A.z);
         if (__any_sync(full, active)) {           // warp-uniform: skip fully inactive stretches
             const float2 cand = candUp ? up : res;
             const float2 g0 = make_float2(B.x, B.y), bl = make_float2(B.z, B.w);
             const float fx = fadd(cand.x, offx), fy = fadd(cand.y, offy);
-            bool bad = false;
-            float v = eval_err<false>(k, (float)x, yf, g0, bl, fx, fy, bad);
-            out = finish_pixel<false>(k, v, gbase, res, up, i > 0, j > 0, A, bad);
-            if (__any_sync(full, bad && active)) {   // rare: an operand left the branch-free range -> IEEE intrinsics
-                bool dummy = false;
-                v = eval_err<true>(k, (float)x, yf, g0, bl, fx, fy, dummy);
-                out = finish_pixel<true>(k, v, gbase, res, up, i > 0, j > 0, A, dummy);
+            unsigned t1 = 0xffffffffu, t2 = 0xffffffffu;
+            float v = eval_err<POSX, false>(k, xf, yf, g0, bl, fx, fy, t1);
+            out = finish_pixel<false>(k, v, gbase, res, up, i > 0, j > 0, A, t2);
+            // operands left the range of the branch-free sequences (tiny non-zero, or huge / inf / NaN)?
+            const bool bad = (min(t1, t2) < PF_TINY_BITS - 1u) || !(v < 0x1p50f);
+            if (__any_sync(full, bad && active)) {   // rare: redo this step with the IEEE intrinsics
+                v = eval_err<POSX, true>(k, xf, yf, g0, bl, fx, fy, t1);
+                out = finish_pixel<true>(k, v, gbase, res, up, i > 0, j > 0, A, t2);
             }
         }
-        if (valid) {
-            res = out;
-            if (kk == 0) {
-                if (active) a.flow[(size_t)y * w + x] = out;    // inactive pixels keep their flow
-                if (g == SW_ROWS_PER_WARP - 1 && ll_out != nullptr) {
-                    const uint4 v = make_uint4(__float_as_uint(out.x), 1u, __float_as_uint(out.y), 1u);
-                    if (out_sh) ll_store_shared(ll_out + i, v); else ll_store_global(ll_out + i, v);
+        if (valid) res = out;
+        if (kk == 0) {
+            const int x = DIR > 0 ? i : w - 1 - i;
+            if (active) flow_row[x] = out;        // inactive pixels keep their flow
+            if (g == SW_ROWS_PER_WARP - 1 && has_out && valid) {
+                if (out_global) {
+                    ll_store_global(gout + i, make_uint4(__float_as_uint(out.x), 1u, __float_as_uint(out.y), 1u));
+                } else {
+                    while (i >= out_limit) out_limit = ld_volatile_shared_s32(prog_out) + SW_LL_RING;   // back-pressure
+                    const unsigned e = (unsigned)(i / SW_LL_RING) + 1u;
+                    ll_store_shared(rout + (i & (SW_LL_RING - 1)) * 16, make_uint4(__float_as_uint(out.x), e, __float_as_uint(out.y), e));
                 }
             }
         }
+        xf = fadd(xf, (float)DIR);
     }
     cp_async_wait<0>();
 }
 
-size_t sweep2_boundary_lines(int h, int w, bool smem_ll) {
+size_t sweep2_boundary_lines(int h, int w, bool) {
     const int ncta = (h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
-    const int nwarp = ncta * SW_WARPS;
-    const int n = smem_ll ? ncta - 1 : nwarp - 1;
-    return (size_t)(n > 0 ? n : 0) * (size_t)w + 1;
+    return (size_t)(ncta > 1 ? ncta - 1 : 0) * (size_t)w + 1;
 }
 
-bool sweep2_use_smem(int w) { return (size_t)SW_WARPS * w * sizeof(uint4) <= 180 * 1024; }
+bool sweep2_use_smem(int) { return true; }
 
 void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st) {
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {   // opt in to > 48 KB of dynamic shared memory, once per device
-        cudaFuncSetAttribute(k_sweep3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_sweep3<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set[dev] = true;
-    }
     const int ncta = (a.s.h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
-    const size_t smem = a.smem_ll ? (size_t)SW_WARPS * a.s.w * sizeof(uint4) : 0;
-    if (dir > 0) k_sweep3<1><<<ncta, SW_THREADS, smem, st>>>(a);
-    else k_sweep3<-1><<<ncta, SW_THREADS, smem, st>>>(a);
+    if (dir > 0) {
+        if (a.s.posx) k_sweep5<1, 1><<<ncta, SW_THREADS, 0, st>>>(a); else k_sweep5<1, 0><<<ncta, SW_THREADS, 0, st>>>(a);
+    } else {
+        if (a.s.posx) k_sweep5<-1, 1><<<ncta, SW_THREADS, 0, st>>>(a); else k_sweep5<-1, 0><<<ncta, SW_THREADS, 0, st>>>(a);
+    }
 }
 
 }  // namespace pf
