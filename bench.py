@@ -21,7 +21,11 @@ import sys
 import tempfile
 import time
 
-import numpy as np
+# One hardware work queue per stream of the engine (3 streams per pair in flight): without this, streams share
+# queues and kernels of independent pairs serialise behind each other.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:

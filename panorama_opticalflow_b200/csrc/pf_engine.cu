@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <cstdlib>
 #include <mutex>
 #include <string>
@@ -500,6 +501,7 @@ int pf_prepare_bidirectional_batch(pf_engine* e, int n, const void* const* Ls, s
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard g(e->device);
     std::vector<Workspace*> used;
+    const auto t_begin = std::chrono::steady_clock::now();
     const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};   // CPU/OpticalFlow.cpp:130-139
     for (int i = 0; i < n; ++i) {
         Workspace* w;
@@ -510,8 +512,15 @@ int pf_prepare_bidirectional_batch(pf_engine* e, int n, const void* const* Ls, s
         const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
         if ((rc = enqueue_pair(e, *w, Ls[i], sl, Rs[i], sr, 2, hints, outs, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
     }
+    const auto t_enq = std::chrono::steady_clock::now();
     for (Workspace* w : used)
         if ((rc = sync_pair(*w, 2)) != PF_OK) return rc;
+    if (getenv("PF_DEBUG_TIMING")) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pf] batch n=%d: enqueue %.2f ms, wait %.2f ms\n", n,
+                std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
+                std::chrono::duration<double, std::milli>(t_end - t_enq).count());
+    }
     return collect_sweep_timing(e, used);
 }
 

@@ -35,6 +35,9 @@
 //     one warp, so throughput comes from interleaving independent wavefronts on the same schedulers.  CTAs take
 //     their row block from an atomic ticket, so block b is always resident before block b+1 spins (no deadlock
 //     whatever the residency).
+#include <cstdlib>
+#include <type_traits>
+
 #include "pf_kernels.cuh"
 #include "pf_math.cuh"
 
@@ -92,22 +95,29 @@ void launch_skew_copy_f2(const float2* src, float2* dst, const Skew& s, cudaStre
 // ---------------------------------------------------------------------------------------------------------
 // sweep prep: everything that depends only on the pixel's own old flow (fully parallel).
 //
-// Output layout ("wavefront-packed"): the sweep gives 4 consecutive logical rows to a warp and at step s row g
+// Output layout ("wavefront-packed"): the sweep gives R consecutive logical rows to a warp and at step s row g
 // of the warp handles logical column s-g.  Record (A,B) of that pixel is stored at
-//     rec[((wb * nsteps + s) * 4 + g)]            wb = logical row / 4, nsteps = w + 3
-// so everything one warp needs for one step is ONE 128-byte line and a warp consumes its lines strictly
-// sequentially -- which is what lets the sweep stage them through shared memory with cp.async many steps ahead.
+//     rec[((wb * nsteps + s) * R + g)]            wb = logical row / R, nsteps = w + R - 1
+// (R = rows per warp: 4, 16 or 32) so everything one warp needs for one step is ONE contiguous run of R*32 bytes
+// and a warp consumes its runs strictly sequentially -- which is what lets the sweep stage them through shared
+// memory with cp.async several steps ahead.
 // ---------------------------------------------------------------------------------------------------------
 size_t sweep_rec_count(int h, int w) {
-    const size_t nblk = (size_t)(h + SW_ROWS_PER_WARP_C - 1) / SW_ROWS_PER_WARP_C;
-    return (nblk * (size_t)(w + SW_ROWS_PER_WARP_C - 1) + SW_STREAM_DEPTH_C + 1) * SW_ROWS_PER_WARP_C;
+    // worst case over the supported rows-per-warp values (4, 16, 32), plus the cp.async lookahead
+    size_t best = 0;
+    for (int R = 4; R <= 32; R *= 2) {
+        const size_t nblk = (size_t)(h + R - 1) / R;
+        const size_t n = (nblk * (size_t)(w + R - 1) + 16) * R;
+        if (n > best) best = n;
+    }
+    return best;
 }
 
 template <int DIR>
 __global__ void __launch_bounds__(256)
 k_sweep_prep(const float* __restrict__ alpha0, const float* __restrict__ alpha1, const float2* __restrict__ G0,
              const float2* __restrict__ G1, const float2* __restrict__ blurred, const float2* __restrict__ flow,
-             SweepRec* __restrict__ rec, int h, int w) {
+             SweepRec* __restrict__ rec, int h, int w, int R) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
@@ -128,8 +138,8 @@ k_sweep_prep(const float* __restrict__ alpha0, const float* __restrict__ alpha1,
         A.z = fsub(f.y, fmul(PF_GRAD_STEP, __fdiv_rn(fsub(ey, e0), PF_GRAD_EPS)));
     }
     const int j = DIR > 0 ? y : h - 1 - y, i = DIR > 0 ? x : w - 1 - x;
-    const int wb = j / SW_ROWS_PER_WARP_C, g = j % SW_ROWS_PER_WARP_C;
-    const size_t idx = ((size_t)wb * (w + SW_ROWS_PER_WARP_C - 1) + (i + g)) * SW_ROWS_PER_WARP_C + g;
+    const int wb = j / R, g = j % R;
+    const size_t idx = ((size_t)wb * (w + R - 1) + (i + g)) * R + g;
     SweepRec r;
     r.a = A;
     r.b = make_float4(g0.x, g0.y, bl.x, bl.y);
@@ -139,24 +149,31 @@ k_sweep_prep(const float* __restrict__ alpha0, const float* __restrict__ alpha1,
 void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
                        const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st) {
     dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
-    if (dir > 0) k_sweep_prep<1><<<g, b, 0, st>>>(alpha0, alpha1, G0, G1, blurred, flow, rec, h, w);
-    else k_sweep_prep<-1><<<g, b, 0, st>>>(alpha0, alpha1, G0, G1, blurred, flow, rec, h, w);
+    const int R = 32 / sweep_lanes_per_row();
+    if (dir > 0) k_sweep_prep<1><<<g, b, 0, st>>>(alpha0, alpha1, G0, G1, blurred, flow, rec, h, w, R);
+    else k_sweep_prep<-1><<<g, b, 0, st>>>(alpha0, alpha1, G0, G1, blurred, flow, rec, h, w, R);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // the wavefront sweep
 // ---------------------------------------------------------------------------------------------------------
-constexpr int SW_P = 8;                        // lanes per row
-constexpr int SW_ROWS_PER_WARP = SW_ROWS_PER_WARP_C;    // 4
-static_assert(SW_ROWS_PER_WARP * SW_P == 32, "one warp = 4 rows x 8 lanes");
-constexpr int SW_STREAM_DEPTH = SW_STREAM_DEPTH_C;      // cp.async groups in flight per warp (steps of lookahead)
-constexpr int SW_STREAM_SLOTS = 16;                     // ring slots (power of two > depth)
-constexpr int SW_WARPS = 8;                    // compute warps per CTA (+ 1 poller warp)
-constexpr int SW_ROWS_PER_CTA = SW_ROWS_PER_WARP * SW_WARPS;
-constexpr int SW_THREADS = (SW_WARPS + 1) * 32;
 constexpr int SW_PREFETCH_GATHER = 4;          // steps ahead for the L1 warm-up of the gradient gather
 constexpr int SW_LL_RING = 64;                 // entries of a shared-memory LL ring (power of two)
 constexpr int SW_PROGRESS_EVERY = 8;           // consumer publishes its progress every 8 columns
+
+// Geometry of the sweep kernel for P lanes per row.  P = 8: one error evaluation per lane (shortest chain per
+// step); P = 2: one candidate (3 probes) per lane; P = 1: both candidates (6 probes) per lane -- fewer issue slots
+// per pixel and independent chains for the in-order scheduler to interleave.
+template <int P> struct SweepGeom {
+    static constexpr int ROWS = 32 / P;                       // rows per warp
+    static constexpr int NQ = P == 8 ? 1 : (P == 2 ? 3 : 6);  // evaluations per lane
+    static constexpr int WARPS = P == 8 ? 8 : (P == 2 ? 4 : 2);   // compute warps per CTA (+ 1 poller warp)
+    static constexpr int ROWS_PER_CTA = ROWS * WARPS;
+    static constexpr int THREADS = (WARPS + 1) * 32;
+    static constexpr int DEPTH = P == 8 ? 8 : 4;              // cp.async groups in flight (steps of lookahead)
+    static constexpr int SLOTS = 2 * DEPTH;                   // ring slots
+    static constexpr int CHUNKS = ROWS * 2;                   // 16-byte chunks per step
+};
 
 __device__ __forceinline__ uint4 ll_load_global(const uint4* p) {
     uint4 v;
@@ -250,20 +267,13 @@ __device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float y
     return err;
 }
 
-// From one error per lane to the pixel's result: six shuffles give every lane of the row the errors of both
-// candidates at the three probe offsets; finish both gradient steps (CPU/PixFlow.hpp:321, :364-386) and select in the
-// reference's order (:318-320: left proposal first, then up, strict <).
+// From the six errors {L, L+dx, L+dy, U, U+dx, U+dy} of a pixel to its result: finish both candidates' gradient steps
+// (CPU/PixFlow.hpp:321, :364-386) and select in the reference's order (:318-320: left proposal first, then up, strict <).
 template <bool SLOW>
-__device__ __forceinline__ float2 finish_pixel(const SweepConst& k, float v, int gbase, float2 left, float2 up,
+__device__ __forceinline__ float2 finish_pixel(const SweepConst& k, const float e6[6], float2 left, float2 up,
                                                bool leftValid, bool upValid, float4 A, unsigned& tiny) {
-    const unsigned full = 0xffffffffu;
-    float eL = __shfl_sync(full, v, gbase + 0);
-    const float eLx = __shfl_sync(full, v, gbase + 1);
-    const float eLy = __shfl_sync(full, v, gbase + 2);
-    float eU = __shfl_sync(full, v, gbase + 3);
-    const float eUx = __shfl_sync(full, v, gbase + 4);
-    const float eUy = __shfl_sync(full, v, gbase + 5);
-    const float dLx = fsub(eLx, eL), dLy = fsub(eLy, eL), dUx = fsub(eUx, eU), dUy = fsub(eUy, eU);
+    float eL = e6[0], eU = e6[3];
+    const float dLx = fsub(e6[1], eL), dLy = fsub(e6[2], eL), dUx = fsub(e6[4], eU), dUy = fsub(e6[5], eU);
     float qLx, qLy, qUx, qUy;
     if (SLOW) {
         qLx = __fdiv_rn(dLx, PF_GRAD_EPS); qLy = __fdiv_rn(dLy, PF_GRAD_EPS);
@@ -285,24 +295,25 @@ __device__ __forceinline__ float2 finish_pixel(const SweepConst& k, float v, int
     return out;
 }
 
-template <int DIR, int POSX>
-__global__ void __launch_bounds__(SW_THREADS, 3)
-k_sweep5(Sweep2Args a) {
+template <int DIR, int POSX, int P>
+__global__ void __launch_bounds__(SweepGeom<P>::THREADS)
+k_sweep6(Sweep2Args a) {
+    typedef SweepGeom<P> G;
     __shared__ int s_b;
-    __shared__ int s_progress[SW_WARPS];                                  // columns consumed from ring k
-    __shared__ __align__(16) uint4 s_llring[SW_WARPS][SW_LL_RING];        // [0] inbound via the poller, [k] from warp k-1
-    __shared__ __align__(128) SweepRec s_ring[SW_WARPS][SW_STREAM_SLOTS][SW_ROWS_PER_WARP];   // 16 KB
-    __shared__ uint4 s_touch[SW_WARPS][32];
+    __shared__ int s_progress[G::WARPS];                                  // columns consumed from ring k
+    __shared__ __align__(16) uint4 s_llring[G::WARPS][SW_LL_RING];        // [0] inbound via the poller, [k] from warp k-1
+    __shared__ __align__(128) SweepRec s_ring[G::WARPS][G::SLOTS][G::ROWS];
+    __shared__ uint4 s_touch[G::WARPS][32];
     const unsigned full = 0xffffffffu;
     int w = a.s.w, h = a.s.h;
     if (threadIdx.x == 0) s_b = atomicAdd(a.ticket, 1);
-    for (int i = threadIdx.x; i < SW_WARPS * SW_LL_RING; i += SW_THREADS) (&s_llring[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x < SW_WARPS) s_progress[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < G::WARPS * SW_LL_RING; i += G::THREADS) (&s_llring[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < G::WARPS) s_progress[threadIdx.x] = 0;
     __syncthreads();
     const int b = s_b;
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (wi == SW_WARPS) {
+    if (wi == G::WARPS) {
         // ---- poller warp: forward the upstream CTA's global LL lines into ring 0 as they become valid ----
         if (b == 0) return;
         const uint4* src = a.boundary + (size_t)(b - 1) * w;
@@ -312,33 +323,39 @@ k_sweep5(Sweep2Args a) {
             while (base + 32 > ld_volatile_shared_s32(prog) + SW_LL_RING) { }    // back-pressure: batch must fit
             const int col = base + lane;
             bool done = col >= w;
+            bool started = base > 0;
             while (!__all_sync(full, done)) {
+                bool got = false;
                 if (!done) {
                     const uint4 v = ll_load_global(src + col);
                     if (v.y == 1u && v.w == 1u) {
                         const unsigned e = (unsigned)(col / SW_LL_RING) + 1u;
                         ll_store_shared(ring0 + (col & (SW_LL_RING - 1)) * 16, make_uint4(v.x, e, v.z, e));
-                        done = true;
+                        done = true; got = true;
                     }
+                }
+                if (!started) {                       // upstream CTA not running yet: back off
+                    started = __any_sync(full, got);
+                    if (!started) __nanosleep(256);
                 }
             }
         }
         return;
     }
 
-    const int g = lane >> 3, kk = lane & 7, gbase = lane & 24;
-    const int jw = b * SW_ROWS_PER_CTA + wi * SW_ROWS_PER_WARP;    // first logical row of this warp
+    const int g = lane / P, sub = lane % P, gbase = lane - sub;
+    const int jw = b * G::ROWS_PER_CTA + wi * G::ROWS;            // first logical row of this warp
     if (jw >= h) return;
     const int j = jw + g;
     const bool rowValid = j < h;
     const int y = DIR > 0 ? j : h - 1 - j;
     const bool has_in = jw > 0;                                    // warp-uniform
-    const bool has_out = jw + SW_ROWS_PER_WARP < h;                // warp-uniform
-    const bool out_global = wi == SW_WARPS - 1;
+    const bool has_out = jw + G::ROWS < h;                         // warp-uniform
+    const bool out_global = wi == G::WARPS - 1;
     const unsigned rin = smem_u32(&s_llring[wi][0]);
-    const unsigned rout = smem_u32(&s_llring[(wi + 1) & (SW_WARPS - 1)][0]);
+    const unsigned rout = smem_u32(&s_llring[(wi + 1) % G::WARPS][0]);
     const unsigned prog_in = smem_u32(&s_progress[wi]);
-    const unsigned prog_out = smem_u32(&s_progress[(wi + 1) & (SW_WARPS - 1)]);
+    const unsigned prog_out = smem_u32(&s_progress[(wi + 1) % G::WARPS]);
     uint4* gout = a.boundary + (size_t)b * w;
     int out_limit = SW_LL_RING;                                    // columns < out_limit fit in the out ring unchecked
 
@@ -352,42 +369,50 @@ k_sweep5(Sweep2Args a) {
     asm volatile("" : "+r"(w), "+r"(k.pitch), "+r"(k.dstep), "+r"(k.g1s_last));     // keep loop invariants in registers
     asm volatile("" : "+f"(k.wm2), "+f"(k.hm2), "+f"(k.fw), "+f"(k.rcp_w), "+f"(k.rcp_eps));
     const float NEG_INF = __int_as_float(0xff800000);
-    // this lane's probe: lanes 0-2 left candidate, 3-5 up candidate (6, 7 duplicate 3, 4), offsets (0,0) (eps,0) (0,eps)
-    const bool candUp = kk >= 3;
-    const int probe = kk % 3;
-    const float offx = probe == 1 ? PF_GRAD_EPS : 0.0f, offy = probe == 2 ? PF_GRAD_EPS : 0.0f;
+    // P = 8: this lane's single probe (lanes 0-2 left candidate, 3-5 up candidate, 6-7 duplicates of 3-4)
+    const bool candUp8 = sub >= 3;
+    const float offx8 = (sub % 3) == 1 ? PF_GRAD_EPS : 0.0f, offy8 = (sub % 3) == 2 ? PF_GRAD_EPS : 0.0f;
     const float yf = (float)y;
     float xf = (float)(DIR > 0 ? -g : w - 1 + g);                  // float(x) of step 0, then +-1 per step (exact)
     float2* flow_row = a.flow + (size_t)y * w;
 
-    // ---- record stream: one 128-byte line per step, staged through a shared-memory ring with cp.async ----
-    const int nsteps = w + SW_ROWS_PER_WARP - 1;
-    const uint4* stream = reinterpret_cast<const uint4*>(a.rec + (size_t)(jw / SW_ROWS_PER_WARP) * nsteps * SW_ROWS_PER_WARP) + lane;
-    const unsigned ring = smem_u32(&s_ring[wi][0][0]);             // 128 bytes per slot
-    for (int t = 0; t < SW_STREAM_DEPTH; ++t) {                    // prologue: steps 0 .. depth-1
-        if (lane < 8) cp_async16(ring + (t & (SW_STREAM_SLOTS - 1)) * 128 + lane * 16, stream + (size_t)t * 8);
+    // ---- record stream: ROWS*32 contiguous bytes per step, staged through a shared-memory ring with cp.async ----
+    const int nsteps = w + G::ROWS - 1;
+    const uint4* stream = reinterpret_cast<const uint4*>(a.rec + (size_t)(jw / G::ROWS) * nsteps * G::ROWS);
+    const unsigned ring = smem_u32(&s_ring[wi][0][0]);
+    auto issue = [&](int t) {
+        const unsigned dst = ring + (t % G::SLOTS) * (G::CHUNKS * 16);
+        const uint4* src = stream + (size_t)t * G::CHUNKS;
+#pragma unroll
+        for (int c0 = 0; c0 < G::CHUNKS; c0 += 32)
+            if (c0 + lane < G::CHUNKS) cp_async16(dst + (c0 + lane) * 16, src + c0 + lane);
         cp_async_commit();
-    }
+    };
+    for (int t = 0; t < G::DEPTH; ++t) issue(t);                   // prologue: steps 0 .. depth-1
     const uint4* s_slot0 = reinterpret_cast<const uint4*>(&s_ring[wi][0][g]);
 
     float2 res = make_float2(0.0f, 0.0f);
     uint4 ln = make_uint4(0u, 0u, 0u, 0u);
-    if (has_in) ln = ll_load_shared(rin);
+    if (has_in) {
+        // Waiting for this warp's turn (the wavefront reaches row jw after ~jw steps): sleep-poll so that the
+        // warps still queued behind the front leave the issue slots to the warps that are working.
+        ln = ll_load_shared(rin);
+        while (ln.y != 1u || ln.w != 1u) { __nanosleep(128); ln = ll_load_shared(rin); }
+    }
 
     for (int s = 0; s < nsteps; ++s) {
         const int i = s - g;                      // logical column of this row at this step
-        // ---- records: issue the line of step s+depth, wait for the line of step s ----
-        if (lane < 8) cp_async16(ring + ((s + SW_STREAM_DEPTH) & (SW_STREAM_SLOTS - 1)) * 128 + lane * 16, stream + (size_t)(s + SW_STREAM_DEPTH) * 8);
-        cp_async_commit();
-        cp_async_wait<SW_STREAM_DEPTH>();
+        // ---- records: issue the run of step s+depth, wait for the run of step s ----
+        issue(s + G::DEPTH);
+        cp_async_wait<G::DEPTH>();
         __syncwarp();
-        const uint4* slot = s_slot0 + (s & (SW_STREAM_SLOTS - 1)) * 8;
+        const uint4* slot = s_slot0 + (s % G::SLOTS) * G::CHUNKS;
         const float4 A = *reinterpret_cast<const float4*>(slot);
         const float4 B = *reinterpret_cast<const float4*>(slot + 1);
         // ---- up neighbour: previous result of the row above (shuffle; first row of the warp: LL ring) ----
         float2 up;
-        up.x = __shfl_up_sync(full, res.x, SW_P);
-        up.y = __shfl_up_sync(full, res.y, SW_P);
+        up.x = __shfl_up_sync(full, res.x, P);
+        up.y = __shfl_up_sync(full, res.y, P);
         if (has_in && s < w) {                    // warp-uniform: every lane reads the same ring entry
             const unsigned e = (unsigned)(s / SW_LL_RING) + 1u;
             uint4 v = ln;
@@ -400,24 +425,58 @@ k_sweep5(Sweep2Args a) {
         const bool active = valid && A.x > NEG_INF;
         float2 out = make_float2(A.y, A.z);
         if (__any_sync(full, active)) {           // warp-uniform: skip fully inactive stretches
-            const float2 cand = candUp ? up : res;
             const float2 g0 = make_float2(B.x, B.y), bl = make_float2(B.z, B.w);
-            const float fx = fadd(cand.x, offx), fy = fadd(cand.y, offy);
-            unsigned t1 = 0xffffffffu, t2 = 0xffffffffu;
-            float v = eval_err<POSX, false>(k, xf, yf, g0, bl, fx, fy, t1);
-            out = finish_pixel<false>(k, v, gbase, res, up, i > 0, j > 0, A, t2);
+            float v[G::NQ];
+            unsigned tkey = 0xffffffffu;
+            float vmax = 0.0f;
+            auto run = [&](auto slow_tag) {
+                constexpr bool SLOW = decltype(slow_tag)::value;
+#pragma unroll
+                for (int q = 0; q < G::NQ; ++q) {
+                    bool cu; float ox, oy;
+                    if (P == 8) { cu = candUp8; ox = offx8; oy = offy8; }
+                    else {
+                        const int probe = q % 3;
+                        cu = P == 2 ? (sub != 0) : (q >= 3);
+                        ox = probe == 1 ? PF_GRAD_EPS : 0.0f; oy = probe == 2 ? PF_GRAD_EPS : 0.0f;
+                    }
+                    const float2 cand = cu ? up : res;
+                    unsigned t1 = 0xffffffffu;
+                    v[q] = eval_err<POSX, SLOW>(k, xf, yf, g0, bl, fadd(cand.x, ox), fadd(cand.y, oy), t1);
+                    tkey = min(tkey, t1);
+                    vmax = fmaxf(vmax, fabsf(v[q]));
+                    if (!(v[q] == v[q])) vmax = __int_as_float(0x7f800000);      // NaN -> flagged
+                }
+                // every lane of the row gets the six errors {L, L+dx, L+dy, U, U+dx, U+dy}
+                float e6[6];
+                if (P == 8) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) e6[q] = __shfl_sync(full, v[0], gbase + q);
+                } else if (P == 2) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const float o = __shfl_xor_sync(full, v[q], 1);
+                        e6[q] = sub == 0 ? v[q] : o;
+                        e6[3 + q] = sub == 0 ? o : v[q];
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) e6[q] = v[q % G::NQ];
+                }
+                unsigned t2 = 0xffffffffu;
+                out = finish_pixel<SLOW>(k, e6, res, up, i > 0, j > 0, A, t2);
+                tkey = min(tkey, t2);
+            };
+            run(std::false_type());
             // operands left the range of the branch-free sequences (tiny non-zero, or huge / inf / NaN)?
-            const bool bad = (min(t1, t2) < PF_TINY_BITS - 1u) || !(v < 0x1p50f);
-            if (__any_sync(full, bad && active)) {   // rare: redo this step with the IEEE intrinsics
-                v = eval_err<POSX, true>(k, xf, yf, g0, bl, fx, fy, t1);
-                out = finish_pixel<true>(k, v, gbase, res, up, i > 0, j > 0, A, t2);
-            }
+            const bool bad = (tkey < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f);
+            if (__any_sync(full, bad && active)) run(std::true_type());   // rare: redo the step with the IEEE intrinsics
         }
         if (valid) res = out;
-        if (kk == 0) {
+        if (sub == 0) {
             const int x = DIR > 0 ? i : w - 1 - i;
             if (active) flow_row[x] = out;        // inactive pixels keep their flow
-            if (g == SW_ROWS_PER_WARP - 1 && has_out && valid) {
+            if (g == G::ROWS - 1 && has_out && valid) {
                 if (out_global) {
                     ll_store_global(gout + i, make_uint4(__float_as_uint(out.x), 1u, __float_as_uint(out.y), 1u));
                 } else {
@@ -432,19 +491,48 @@ k_sweep5(Sweep2Args a) {
     cp_async_wait<0>();
 }
 
+// lanes per row of the sweep kernel: 8 (default; lowest latency per step), 2 or 1 (fewer issue slots per pixel).
+// PF_SWEEP_LANES overrides; read once.
+int sweep_lanes_per_row() {
+    static int p = 0;
+    if (p == 0) {
+        const char* e = getenv("PF_SWEEP_LANES");
+        const int v = e ? atoi(e) : 8;
+        p = (v == 1 || v == 2 || v == 8) ? v : 8;
+    }
+    return p;
+}
+
+static int rows_per_cta() {
+    const int p = sweep_lanes_per_row();
+    return p == 8 ? SweepGeom<8>::ROWS_PER_CTA : (p == 2 ? SweepGeom<2>::ROWS_PER_CTA : SweepGeom<1>::ROWS_PER_CTA);
+}
+
 size_t sweep2_boundary_lines(int h, int w, bool) {
-    const int ncta = (h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
+    // sized for the smallest CTA (32 rows), whatever PF_SWEEP_LANES says
+    const int ncta = (h + 31) / 32;
     return (size_t)(ncta > 1 ? ncta - 1 : 0) * (size_t)w + 1;
 }
 
 bool sweep2_use_smem(int) { return true; }
 
-void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st) {
-    const int ncta = (a.s.h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
+template <int P>
+static void launch_sweep_p(const Sweep2Args& a, int dir, cudaStream_t st) {
+    typedef SweepGeom<P> G;
+    const int ncta = (a.s.h + G::ROWS_PER_CTA - 1) / G::ROWS_PER_CTA;
     if (dir > 0) {
-        if (a.s.posx) k_sweep5<1, 1><<<ncta, SW_THREADS, 0, st>>>(a); else k_sweep5<1, 0><<<ncta, SW_THREADS, 0, st>>>(a);
+        if (a.s.posx) k_sweep6<1, 1, P><<<ncta, G::THREADS, 0, st>>>(a); else k_sweep6<1, 0, P><<<ncta, G::THREADS, 0, st>>>(a);
     } else {
-        if (a.s.posx) k_sweep5<-1, 1><<<ncta, SW_THREADS, 0, st>>>(a); else k_sweep5<-1, 0><<<ncta, SW_THREADS, 0, st>>>(a);
+        if (a.s.posx) k_sweep6<-1, 1, P><<<ncta, G::THREADS, 0, st>>>(a); else k_sweep6<-1, 0, P><<<ncta, G::THREADS, 0, st>>>(a);
+    }
+}
+
+void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st) {
+    (void)rows_per_cta;
+    switch (sweep_lanes_per_row()) {
+    case 1: launch_sweep_p<1>(a, dir, st); break;
+    case 2: launch_sweep_p<2>(a, dir, st); break;
+    default: launch_sweep_p<8>(a, dir, st); break;
     }
 }
 
