@@ -59,6 +59,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def pair_shifts(rank, batch):
+    """Row shifts that derive this rank's `batch` pairs from the shared base pair: disjoint across ranks."""
+    return [37 * (rank * batch + i) for i in range(batch)]
+
+
+def aggregate_mpix(world, batch, rows, cols, ms_per_step):
+    """Whole-job throughput: units processed by ALL ranks per step / (max-over-ranks) step time."""
+    return world * batch * rows * cols / 1e6 / (ms_per_step / 1e3)
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -174,7 +184,7 @@ def run_b200(args, rank, world, local_rank):
         base[0].copy_(torch.from_numpy(L)); base[1].copy_(torch.from_numpy(R))
     if dist is not None:
         dist.broadcast(base, src=0)
-    shifts = [37 * (rank * B + i) for i in range(B)]
+    shifts = pair_shifts(rank, B)
     dL = [torch.roll(base[0], s, dims=0).contiguous() for s in shifts]
     dR = [torch.roll(base[1], s, dims=0).contiguous() for s in shifts]
     oLR = [torch.empty((rows, cols, 2), dtype=torch.float32, device="cuda") for _ in range(B)]
@@ -208,6 +218,11 @@ def run_b200(args, rank, world, local_rank):
     step_dev = lambda: eng.prepareBidirectionalBatch(dL, dR, oLR, oRL)
     for _ in range(args.warmup):
         step_dev()
+    # latency of ONE pair (BASELINE configs[1] read literally), for the record next to the batched throughput
+    step_one = lambda: eng.prepareBidirectionalBatch(dL[:1], dR[:1], oLR[:1], oRL[:1])
+    step_one()
+    one_ms, _ = timed(step_one, 2)
+    one_ms /= 2
     sampler = ClockSampler()
     if rank == 0:
         sampler.start()
@@ -215,7 +230,7 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     mpix_step = world * B * rows * cols / 1e6
-    value = mpix_step / (ms_step / 1e3)
+    value = aggregate_mpix(world, B, rows, cols, ms_step)
 
     # ---- end to end through the same C-ABI call with pinned HOST buffers ----
     hL = [torch.empty((rows, cols, 4), dtype=torch.uint8).pin_memory() for _ in range(B)]
@@ -272,7 +287,9 @@ def run_b200(args, rank, world, local_rank):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "%s bidirectional flow (NovelViewGeneratorAsymmetricFlow::prepare semantics) on synthetic %d x %d (rows x cols) BGRA overlap pairs, disparity amplitude %.0f px" % (args.preset, rows, cols, amp),
-                   "rows": rows, "cols": cols, "pairs_per_step_per_gpu": B, "parallelism": "replicas x%d (pairs are independent; NCCL broadcast of the base pair at set-up only)" % world,
+                   "rows": rows, "cols": cols, "pairs_per_step_per_gpu": B, "single_pair_latency_ms": one_ms,
+                   "single_pair_mpix_s": rows * cols / 1e6 / (one_ms / 1e3), "sweep_lanes_per_row": int(os.environ.get("PF_SWEEP_LANES", "2")),
+                   "parallelism": "replicas x%d (pairs are independent; NCCL broadcast of the base pair at set-up only)" % world,
                    "l2": "working set ~0.7 GB per pair >> 126 MB L2, no flush needed", "timing": "CUDA events (pf_timer_*), barrier+sync both sides, max over ranks",
                    "e2e_outputs_match_device_run": bool(same)},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
@@ -292,7 +309,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="independent pairs in flight per GPU per step")
+    ap.add_argument("--batch", type=int, default=8, help="independent pairs in flight per GPU per step")
     ap.add_argument("--rows", type=int, default=4000)
     ap.add_argument("--cols", type=int, default=2000)
     ap.add_argument("--preset", default="pixflow_search_20")

@@ -42,7 +42,7 @@ void launch_skew_copy_f2(const float2* src, float2* dst, const Skew& s, cudaStre
 // per-pixel records for one sweep, in the wavefront-packed layout the sweep streams through shared memory:
 // a = {E(f0), r0.x, r0.y, -} (own-flow terms; {-inf, f0} where alpha <= 0.9), b = {I0x, I0y, blurred.x, blurred.y}.
 struct __align__(16) SweepRec { float4 a, b; };
-int sweep_lanes_per_row();                // 8 (default), 2 or 1; env PF_SWEEP_LANES
+int sweep_lanes_per_row();                // 2 (default), 8 or 1; env PF_SWEEP_LANES
 size_t sweep_rec_count(int h, int w);     // SweepRec elements a (h x w) level needs
 void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
                        const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st);

@@ -491,14 +491,15 @@ k_sweep6(Sweep2Args a) {
     cp_async_wait<0>();
 }
 
-// lanes per row of the sweep kernel: 8 (default; lowest latency per step), 2 or 1 (fewer issue slots per pixel).
+// lanes per row of the sweep kernel: 2 (default: measured equal step latency to 8 with a quarter of the warps and
+// a third of the issue slots per pixel, hence the best throughput when several pairs are in flight), 8 or 1.
 // PF_SWEEP_LANES overrides; read once.
 int sweep_lanes_per_row() {
     static int p = 0;
     if (p == 0) {
         const char* e = getenv("PF_SWEEP_LANES");
-        const int v = e ? atoi(e) : 8;
-        p = (v == 1 || v == 2 || v == 8) ? v : 8;
+        const int v = e ? atoi(e) : 2;
+        p = (v == 1 || v == 2 || v == 8) ? v : 2;
     }
     return p;
 }
