@@ -309,7 +309,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="independent pairs in flight per GPU per step")
+    ap.add_argument("--batch", type=int, default=16, help="independent pairs in flight per GPU per step")
     ap.add_argument("--rows", type=int, default=4000)
     ap.add_argument("--cols", type=int, default=2000)
     ap.add_argument("--preset", default="pixflow_search_20")

@@ -112,9 +112,15 @@ struct Workspace {
     cudaEvent_t evReady = nullptr, evDone[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> sweepEv[2];          // optional timing events
     size_t nSweepEv[2] = {0, 0};
+    // the whole pair pipeline (front end -> both directions -> join) captured once as a CUDA graph and replayed
+    // with a single launch: ~1000 kernel launches per pair would otherwise cost ~3 ms of host time each call
+    cudaGraphExec_t graph = nullptr;
+    uint64_t graph_launches = 0;                  // kernels per replay
+    int graph_key = -1;                           // ndir | hint0 << 4 | hint1 << 8 | search_dist << 12
 
     ~Workspace() { release(); }
     void release() {
+        if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; graph_key = -1; }
         for (int k = 0; k < 2; ++k) {
             cudaFree(in[k]); cudaFree(I[k]); cudaFree(A[k]); cudaFree(G[k]); cudaFree(Gs[k]); cudaFree(rec[k]);
             Gs[k] = nullptr; rec[k] = nullptr;
@@ -130,7 +136,6 @@ struct Workspace {
         }
         cudaFree(Ipre); cudaFree(merged); cudaFree(blend);
         Ipre = nullptr; merged = nullptr; blend = nullptr;
-        if (sMain) cudaStreamDestroy(sMain);
         if (evReady) cudaEventDestroy(evReady);
         sMain = nullptr; evReady = nullptr;
     }
@@ -158,7 +163,7 @@ struct Workspace {
             PF_CUDA(cudaEventCreateWithFlags(&evDone[k], cudaEventDisableTiming));
         }
         PF_CUDA(cudaMalloc(&Ipre, px0 * sizeof(float)));
-        PF_CUDA(cudaStreamCreateWithFlags(&sMain, cudaStreamNonBlocking));
+        sMain = sDir[0];   // the shared front end runs on direction 0's stream: two streams (hardware queues) per pair
         PF_CUDA(cudaEventCreateWithFlags(&evReady, cudaEventDisableTiming));
         return PF_OK;
     }
@@ -171,6 +176,7 @@ struct pf_engine {
     int max_percentage = 0;     // template parameter of PixFlow<MaxPercentage>
     int search_dist = 0;        // computeSearchDistance, CPU/PixFlow.hpp:153-155
     bool time_sweeps = false;
+    bool use_graphs = true;     // PF_NO_GRAPHS=1 disables (per-kernel stream launches, used when timing the sweeps)
     double last_sweep_ms = 0.0;
     uint64_t last_sweep_launches = 0;
     std::mutex mu;
@@ -339,10 +345,11 @@ int check_image_args(const void* p, size_t stride, int rows, int cols, size_t el
 }
 
 // stage an input image: device pointers are used in place, host pointers are copied into ws.in[k]
-int stage_input(Workspace& w, int k, const void* img, size_t stride, const uint8_t** dptr, size_t* dstride, cudaStream_t st) {
-    if (is_device_ptr(img)) { *dptr = (const uint8_t*)img; *dstride = stride; return PF_OK; }
+int stage_input(Workspace& w, int k, const void* img, size_t stride, const uint8_t** dptr, size_t* dstride, cudaStream_t st,
+                bool force_copy = false) {
+    if (!force_copy && is_device_ptr(img)) { *dptr = (const uint8_t*)img; *dstride = stride; return PF_OK; }
     const size_t dense = (size_t)w.plan.cols * 4;
-    PF_CUDA(cudaMemcpy2DAsync(w.in[k], dense, img, stride, dense, w.plan.rows, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpy2DAsync(w.in[k], dense, img, stride, dense, w.plan.rows, cudaMemcpyDefault, st));
     *dptr = w.in[k]; *dstride = dense;
     return PF_OK;
 }
@@ -352,6 +359,47 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
                  int ndir, const int hints[2], void* outs[2], const size_t ostrides[2],
                  const uint8_t* dimg[2], size_t dstride[2], float2* dflow[2], size_t dfstride[2]) {
     int rc;
+    if (e->use_graphs && !e->time_sweeps) {
+        // ---- graph path: inputs -> staging buffers, one graph launch, outputs <- workspace flow buffers ----
+        cudaStream_t st = w.sDir[0];
+        if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], st, true)) != PF_OK) return rc;
+        if ((rc = stage_input(w, 1, imgR, strideR, &dimg[1], &dstride[1], st, true)) != PF_OK) return rc;
+        const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12);
+        if (w.graph_key != key) {
+            if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; w.graph_key = -1; }
+            const uint64_t launched_before = g_launches.load();
+            PF_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            rc = enqueue_shared(e, w, dimg, dstride);
+            for (int d = 0; d < ndir && rc == PF_OK; ++d)
+                rc = enqueue_direction(e, w, d, d == 0 ? 0 : 1, hints[d], w.out[d], (size_t)w.plan.cols * sizeof(float2));
+            if (rc == PF_OK && ndir == 2) {      // join direction 1 back into the capturing stream
+                if (cudaEventRecord(w.evDone[1], w.sDir[1]) != cudaSuccess || cudaStreamWaitEvent(st, w.evDone[1], 0) != cudaSuccess)
+                    rc = fail(PF_ERR_CUDA, "graph capture: join failed");
+            }
+            cudaGraph_t g = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc != PF_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) return fail(PF_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ci = cudaGraphInstantiate(&w.graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ci != cudaSuccess) return fail(PF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ci));
+            w.graph_key = key;
+            w.graph_launches = g_launches.load() - launched_before;   // kernels per replay
+            g_launches.store(launched_before);
+        }
+        PF_CUDA(cudaGraphLaunch(w.graph, st));
+        LAUNCHED(w.graph_launches);
+        for (int d = 0; d < ndir; ++d) {
+            dflow[d] = w.out[d];
+            dfstride[d] = (size_t)w.plan.cols * sizeof(float2);
+            if (outs[d])
+                PF_CUDA(cudaMemcpy2DAsync(outs[d], ostrides[d], w.out[d], dfstride[d], (size_t)w.plan.cols * sizeof(float2),
+                                          w.plan.rows, cudaMemcpyDefault, st));
+        }
+        PF_CUDA(cudaEventRecord(w.evDone[0], st));
+        if (ndir == 2) PF_CUDA(cudaEventRecord(w.evDone[1], st));
+        return PF_OK;
+    }
     if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], w.sMain)) != PF_OK) return rc;
     if ((rc = stage_input(w, 1, imgR, strideR, &dimg[1], &dstride[1], w.sMain)) != PF_OK) return rc;
     if ((rc = enqueue_shared(e, w, dimg, dstride)) != PF_OK) return rc;
@@ -408,6 +456,7 @@ int pf_engine_create(const char* name, int device, pf_engine** out) {
     e->device = device;
     e->max_percentage = pct;
     e->search_dist = (24 * pct + 50) / 100;
+    e->use_graphs = getenv("PF_NO_GRAPHS") == nullptr;
     *out = e;
     g_err.clear();
     return PF_OK;

@@ -191,6 +191,18 @@ __device__ __forceinline__ uint4 ll_load_shared(unsigned saddr) {
 __device__ __forceinline__ void ll_store_shared(unsigned saddr, uint4 v) {
     asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// predicated forms (no branch around the store: the step body is latency-bound on a single warp)
+__device__ __forceinline__ void ll_store_global_if(bool p, uint4* ptr, uint4 v) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4}; }"
+                 :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ void ll_store_shared_if(bool p, unsigned saddr, uint4 v) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4}; }"
+                 :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ void st_volatile_shared_s32_if(bool p, unsigned saddr, int v) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.volatile.shared.s32 [%0], %1; }" :: "r"(saddr), "r"(v), "r"((unsigned)p) : "memory");
+}
 __device__ __forceinline__ int ld_volatile_shared_s32(unsigned saddr) {
     int v;
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
@@ -399,27 +411,31 @@ k_sweep6(Sweep2Args a) {
         ln = ll_load_shared(rin);
         while (ln.y != 1u || ln.w != 1u) { __nanosleep(128); ln = ll_load_shared(rin); }
     }
+    const int in_cols = has_in ? w : 0;           // columns to take from the inbound ring
+    const bool ring_out = has_out && !out_global;
+    const bool last_row = g == G::ROWS - 1 && sub == 0;
+    // records of step 0 (software pipeline: the records of step s+1 are fetched from the ring at the end of step s)
+    cp_async_wait<G::DEPTH - 1>();
+    __syncwarp();
+    float4 A = *reinterpret_cast<const float4*>(s_slot0);
+    float4 B = *reinterpret_cast<const float4*>(s_slot0 + 1);
 
+#pragma unroll 2
     for (int s = 0; s < nsteps; ++s) {
         const int i = s - g;                      // logical column of this row at this step
-        // ---- records: issue the run of step s+depth, wait for the run of step s ----
-        issue(s + G::DEPTH);
-        cp_async_wait<G::DEPTH>();
-        __syncwarp();
-        const uint4* slot = s_slot0 + (s % G::SLOTS) * G::CHUNKS;
-        const float4 A = *reinterpret_cast<const float4*>(slot);
-        const float4 B = *reinterpret_cast<const float4*>(slot + 1);
+        issue(s + G::DEPTH);                      // keep `depth` runs in flight
         // ---- up neighbour: previous result of the row above (shuffle; first row of the warp: LL ring) ----
         float2 up;
         up.x = __shfl_up_sync(full, res.x, P);
         up.y = __shfl_up_sync(full, res.y, P);
-        if (has_in && s < w) {                    // warp-uniform: every lane reads the same ring entry
+        if (s < in_cols) {                        // warp-uniform: every lane reads the same ring entry
             const unsigned e = (unsigned)(s / SW_LL_RING) + 1u;
             uint4 v = ln;
             while (v.y != e || v.w != e) v = ll_load_shared(rin + (s & (SW_LL_RING - 1)) * 16);
             ln = ll_load_shared(rin + ((s + 1) & (SW_LL_RING - 1)) * 16);
-            if ((s & (SW_PROGRESS_EVERY - 1)) == SW_PROGRESS_EVERY - 1 && lane == 0) st_volatile_shared_s32(prog_in, s + 1);
-            if (g == 0) { up.x = __uint_as_float(v.x); up.y = __uint_as_float(v.z); }
+            st_volatile_shared_s32_if((s & (SW_PROGRESS_EVERY - 1)) == SW_PROGRESS_EVERY - 1 && lane == 0, prog_in, s + 1);
+            up.x = g == 0 ? __uint_as_float(v.x) : up.x;
+            up.y = g == 0 ? __uint_as_float(v.z) : up.y;
         }
         const bool valid = rowValid && (unsigned)i < (unsigned)w;
         const bool active = valid && A.x > NEG_INF;
@@ -472,21 +488,28 @@ k_sweep6(Sweep2Args a) {
             const bool bad = (tkey < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f);
             if (__any_sync(full, bad && active)) run(std::true_type());   // rare: redo the step with the IEEE intrinsics
         }
-        if (valid) res = out;
-        if (sub == 0) {
-            const int x = DIR > 0 ? i : w - 1 - i;
-            if (active) flow_row[x] = out;        // inactive pixels keep their flow
-            if (g == G::ROWS - 1 && has_out && valid) {
-                if (out_global) {
-                    ll_store_global(gout + i, make_uint4(__float_as_uint(out.x), 1u, __float_as_uint(out.y), 1u));
-                } else {
-                    while (i >= out_limit) out_limit = ld_volatile_shared_s32(prog_out) + SW_LL_RING;   // back-pressure
-                    const unsigned e = (unsigned)(i / SW_LL_RING) + 1u;
-                    ll_store_shared(rout + (i & (SW_LL_RING - 1)) * 16, make_uint4(__float_as_uint(out.x), e, __float_as_uint(out.y), e));
-                }
-            }
+        res.x = valid ? out.x : res.x;
+        res.y = valid ? out.y : res.y;
+        // ---- results: flow (row-major, only where alpha > 0.9) and the hand-off of the warp's last row ----
+        const int x = DIR > 0 ? i : w - 1 - i;
+        if (active && sub == 0) flow_row[x] = out;
+        const int i_last = s - (G::ROWS - 1);                 // column of the warp's last row (warp-uniform)
+        if (ring_out && i_last >= out_limit)                  // back-pressure, rare: wait until the slot is free
+            while (i_last >= out_limit) out_limit = ld_volatile_shared_s32(prog_out) + SW_LL_RING;
+        {
+            const unsigned e = out_global ? 1u : (unsigned)(i_last / SW_LL_RING) + 1u;
+            const uint4 lv = make_uint4(__float_as_uint(out.x), e, __float_as_uint(out.y), e);
+            const bool doit = last_row && valid && has_out;
+            ll_store_global_if(doit && out_global, gout + i, lv);
+            ll_store_shared_if(doit && !out_global, rout + (i_last & (SW_LL_RING - 1)) * 16, lv);
         }
         xf = fadd(xf, (float)DIR);
+        // ---- records of the next step ----
+        cp_async_wait<G::DEPTH - 1>();
+        __syncwarp();
+        const uint4* slot = s_slot0 + ((s + 1) % G::SLOTS) * G::CHUNKS;
+        A = *reinterpret_cast<const float4*>(slot);
+        B = *reinterpret_cast<const float4*>(slot + 1);
     }
     cp_async_wait<0>();
 }
@@ -517,14 +540,45 @@ size_t sweep2_boundary_lines(int h, int w, bool) {
 
 bool sweep2_use_smem(int) { return true; }
 
+// Experiment knob: a dummy dynamic shared-memory request caps the sweep CTAs per SM (PF_SWEEP_CTAS_PER_SM=n).
+// Measured on B200 with 16-32 pairs in flight: capping at 3 or 2 is 9-16 % SLOWER than no cap, so the default is
+// no cap (profiles/r1_batch_scaling.md).
+static size_t sweep_smem_pad(size_t static_smem) {
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        const char* e = getenv("PF_SWEEP_CTAS_PER_SM");
+        per_sm = e ? atoi(e) : 0;
+        if (per_sm < 1 || per_sm > 8) per_sm = 0;     // 0: no cap
+    }
+    if (per_sm == 0) return 0;
+    const size_t budget = (size_t)227 * 1024 / per_sm - 1024;    // per CTA, incl. the 1 KB the driver reserves
+    return budget > static_smem + 1024 ? ((budget - static_smem) & ~(size_t)127) : 0;
+}
+
 template <int P>
 static void launch_sweep_p(const Sweep2Args& a, int dir, cudaStream_t st) {
     typedef SweepGeom<P> G;
     const int ncta = (a.s.h + G::ROWS_PER_CTA - 1) / G::ROWS_PER_CTA;
+    static size_t pad = (size_t)-1;
+    static bool attr_done[64] = {};
+    if (pad == (size_t)-1) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_sweep6<1, 1, P>);
+        pad = sweep_smem_pad(fa.sharedSizeBytes);
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pad > 0 && dev >= 0 && dev < 64 && !attr_done[dev]) {
+        cudaFuncSetAttribute(k_sweep6<1, 1, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        cudaFuncSetAttribute(k_sweep6<1, 0, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        cudaFuncSetAttribute(k_sweep6<-1, 1, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        cudaFuncSetAttribute(k_sweep6<-1, 0, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        attr_done[dev] = true;
+    }
     if (dir > 0) {
-        if (a.s.posx) k_sweep6<1, 1, P><<<ncta, G::THREADS, 0, st>>>(a); else k_sweep6<1, 0, P><<<ncta, G::THREADS, 0, st>>>(a);
+        if (a.s.posx) k_sweep6<1, 1, P><<<ncta, G::THREADS, pad, st>>>(a); else k_sweep6<1, 0, P><<<ncta, G::THREADS, pad, st>>>(a);
     } else {
-        if (a.s.posx) k_sweep6<-1, 1, P><<<ncta, G::THREADS, 0, st>>>(a); else k_sweep6<-1, 0, P><<<ncta, G::THREADS, 0, st>>>(a);
+        if (a.s.posx) k_sweep6<-1, 1, P><<<ncta, G::THREADS, pad, st>>>(a); else k_sweep6<-1, 0, P><<<ncta, G::THREADS, pad, st>>>(a);
     }
 }
 

@@ -146,3 +146,25 @@ def test_full_size_properties(engine_search, engine_low):
     c = (c[0].copy(), c[1].copy())
     s = engine_low.prepareBidirectional(R, L)
     assert np.array_equal(s[0], c[1]) and np.array_equal(s[1], c[0])
+
+
+def test_stream_path_equals_graph_path(orc, engine_search):
+    """The default path replays a captured CUDA graph; with sweep timing enabled the engine enqueues the kernels one
+    by one on its streams.  Both must give the oracle's bits."""
+    from panorama_opticalflow_b200 import synth
+    L, R = synth.make_pair(130, 170, 70, 11.0, True)
+    want = orc.prepare_bidirectional(L, R, 20)
+    g = engine_search.prepareBidirectional(L, R)
+    g = (g[0].copy(), g[1].copy())
+    engine_search.setSweepTiming(True)
+    try:
+        t = engine_search.prepareBidirectional(L, R)
+        ms, n = engine_search.lastSweepMs()
+    finally:
+        engine_search.setSweepTiming(False)
+    assert n > 0 and ms > 0
+    for a, b, c in zip(g, t, want):
+        assert_bit_equal(a, c, "graph path")
+        assert_bit_equal(b, c, "stream path")
+    again = engine_search.prepareBidirectional(L, R)     # replay of the cached graph
+    assert_bit_equal(again[0], want[0], "graph replay")
