@@ -295,7 +295,7 @@ def run_b200(args, rank, world, local_rank):
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * 2 * rows * cols * 4,
                 "d2h_bytes_per_step": world * B * 2 * rows * cols * 8, "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches) * world, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     eng.close()
