@@ -307,22 +307,26 @@ __device__ __forceinline__ float2 finish_pixel(const SweepConst& k, const float 
     return out;
 }
 
-template <int DIR, int POSX, int P>
-__global__ void __launch_bounds__(SweepGeom<P>::THREADS)
-k_sweep6(Sweep2Args a) {
+// Shared memory of one sweep CTA.
+template <int P> struct SweepSmem {
     typedef SweepGeom<P> G;
-    __shared__ int s_b;
-    __shared__ int s_progress[G::WARPS];                                  // columns consumed from ring k
-    __shared__ __align__(16) uint4 s_llring[G::WARPS][SW_LL_RING];        // [0] inbound via the poller, [k] from warp k-1
-    __shared__ __align__(128) SweepRec s_ring[G::WARPS][G::SLOTS][G::ROWS];
-    __shared__ uint4 s_touch[G::WARPS][32];
+    int b;                                                       // row block being processed
+    int progress[G::WARPS];                                      // columns consumed from ring k
+    __align__(16) uint4 llring[G::WARPS][SW_LL_RING];            // [0] inbound via the poller, [k] from warp k-1
+    __align__(128) SweepRec ring[G::WARPS][G::SLOTS][G::ROWS];   // cp.async staging of the record stream
+    uint4 touch[G::WARPS][32];                                   // targets of the L1 warm-up copies
+};
+
+// One row block (ROWS_PER_CTA logical rows) of one sweep, by one CTA.
+template <int DIR, int POSX, int P>
+__device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, const int b) {
+    typedef SweepGeom<P> G;
     const unsigned full = 0xffffffffu;
     int w = a.s.w, h = a.s.h;
-    if (threadIdx.x == 0) s_b = atomicAdd(a.ticket, 1);
-    for (int i = threadIdx.x; i < G::WARPS * SW_LL_RING; i += G::THREADS) (&s_llring[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (threadIdx.x < G::WARPS) s_progress[threadIdx.x] = 0;
-    __syncthreads();
-    const int b = s_b;
+    auto& s_progress = sm.progress;
+    auto& s_llring = sm.llring;
+    auto& s_ring = sm.ring;
+    auto& s_touch = sm.touch;
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (wi == G::WARPS) {
@@ -514,6 +518,28 @@ k_sweep6(Sweep2Args a) {
     cp_async_wait<0>();
 }
 
+// Persistent sweep kernel: the grid holds only about as many CTAs as the wavefront is wide (front + margin); a CTA
+// that finishes its row block takes the next ticket.  Tickets are handed out in row-block order, so the block a CTA
+// waits on is always being processed (or done) -- no deadlock whatever the residency -- and CTAs far behind the
+// front do not occupy registers and shared memory while they would only be waiting for their turn.
+template <int DIR, int POSX, int P>
+__global__ void __launch_bounds__(SweepGeom<P>::THREADS)
+k_sweep6(Sweep2Args a) {
+    typedef SweepGeom<P> G;
+    __shared__ SweepSmem<P> sm;
+    const int nblocks = (a.s.h + G::ROWS_PER_CTA - 1) / G::ROWS_PER_CTA;
+    for (;;) {
+        __syncthreads();                                  // every warp is done with the previous block
+        if (threadIdx.x == 0) sm.b = atomicAdd(a.ticket, 1);
+        for (int i = threadIdx.x; i < G::WARPS * SW_LL_RING; i += G::THREADS) (&sm.llring[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x < G::WARPS) sm.progress[threadIdx.x] = 0;
+        __syncthreads();
+        const int b = sm.b;
+        if (b >= nblocks) break;
+        sweep_block<DIR, POSX, P>(a, sm, b);
+    }
+}
+
 // lanes per row of the sweep kernel: 2 (default: measured equal step latency to 8 with a quarter of the warps and
 // a third of the issue slots per pixel, hence the best throughput when several pairs are in flight), 8 or 1.
 // PF_SWEEP_LANES overrides; read once.
@@ -558,7 +584,9 @@ static size_t sweep_smem_pad(size_t static_smem) {
 template <int P>
 static void launch_sweep_p(const Sweep2Args& a, int dir, cudaStream_t st) {
     typedef SweepGeom<P> G;
-    const int ncta = (a.s.h + G::ROWS_PER_CTA - 1) / G::ROWS_PER_CTA;
+    const int nblocks = (a.s.h + G::ROWS_PER_CTA - 1) / G::ROWS_PER_CTA;
+    const int front = (a.s.w + 2 * G::ROWS_PER_CTA - 1) / G::ROWS_PER_CTA + 2;   // row blocks working at the same time
+    const int ncta = nblocks < front ? nblocks : front;
     static size_t pad = (size_t)-1;
     static bool attr_done[64] = {};
     if (pad == (size_t)-1) {
