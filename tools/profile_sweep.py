@@ -19,7 +19,7 @@ G0 = np.stack([np.sin(xx / 7) * 0.05, np.cos(yy / 9) * 0.05], 2).astype(np.float
 G1 = np.stack([np.sin((xx + 3) / 7) * 0.05, np.cos((yy + 1) / 9) * 0.05], 2).astype(np.float32)
 flow = np.stack([-3 + 0.3 * np.sin(yy / 50), 0.3 * np.cos(xx / 40)], 2).astype(np.float32)
 flow += (rng.standard_normal((h, w, 2)) * 0.05).astype(np.float32)
-one = np.ones((h, w), np.float32)
+one = np.full((h, w), float(os.environ.get("PF_PROFILE_ALPHA", "1")), np.float32)
 for d in ([+1, -1] * reps)[:reps]:
     t = time.time()
     out = stages.sweep(one, one, G0, G1, flow, flow, d)
