@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpixflow_b200.so")
-SOURCES = ["pf_kernels.cu", "pf_sweep.cu", "pf_selftest.cu", "pf_engine.cu"]
-HEADERS = ["pf_kernels.cuh", "pf_math.cuh", os.path.join("..", "..", "include", "pixflow_b200.h")]
+SOURCES = ["pf_kernels.cu", "pf_sweep.cu", "pf_fused.cu", "pf_selftest.cu", "pf_engine.cu"]
+HEADERS = ["pf_kernels.cuh", "pf_math.cuh", "pf_prep.cuh", os.path.join("..", "..", "include", "pixflow_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,7 +44,7 @@ def needs_build():
 def build_lib(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("PF_EXTRA_NVCC_FLAGS", "").split() + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

@@ -21,6 +21,11 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+// A stream capture is invalidated by device-wide synchronising calls made anywhere in the process while it is open
+// (cudaFree, cudaMalloc, cudaDeviceSynchronize ...).  All of this library's captures, allocations and teardowns take
+// this mutex, so engines used from different threads cannot break each other's captures; a capture that is broken by
+// foreign code falls back to plain stream launches for that call.
+std::mutex g_capture_mu;
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -100,7 +105,6 @@ struct Workspace {
     pf::SweepRec* rec[2] = {nullptr, nullptr};    // per direction: wavefront-packed records of the current sweep
     float2* bufA[2] = {nullptr, nullptr};         // per direction: flow ping
     float2* bufB[2] = {nullptr, nullptr};         // flow pong
-    float2* bufT[2] = {nullptr, nullptr};         // blur row-pass temp
     float2* blurred[2] = {nullptr, nullptr};
     float* ratio[2] = {nullptr, nullptr};
     uint4* bnd[2] = {nullptr, nullptr};
@@ -124,9 +128,9 @@ struct Workspace {
         for (int k = 0; k < 2; ++k) {
             cudaFree(in[k]); cudaFree(I[k]); cudaFree(A[k]); cudaFree(G[k]); cudaFree(Gs[k]); cudaFree(rec[k]);
             Gs[k] = nullptr; rec[k] = nullptr;
-            cudaFree(bufA[k]); cudaFree(bufB[k]); cudaFree(bufT[k]); cudaFree(blurred[k]);
+            cudaFree(bufA[k]); cudaFree(bufB[k]); cudaFree(blurred[k]);
             cudaFree(ratio[k]); cudaFree(bnd[k]); cudaFree(tickets[k]); cudaFree(out[k]);
-            in[k] = nullptr; I[k] = A[k] = nullptr; G[k] = nullptr; bufA[k] = bufB[k] = bufT[k] = blurred[k] = nullptr;
+            in[k] = nullptr; I[k] = A[k] = nullptr; G[k] = nullptr; bufA[k] = bufB[k] = blurred[k] = nullptr;
             ratio[k] = nullptr; bnd[k] = nullptr; tickets[k] = nullptr; out[k] = nullptr;
             if (sDir[k]) cudaStreamDestroy(sDir[k]);
             if (evDone[k]) cudaEventDestroy(evDone[k]);
@@ -153,7 +157,6 @@ struct Workspace {
             PF_CUDA(cudaMalloc(&rec[k], pf::sweep_rec_count(p.dh, p.dw) * sizeof(pf::SweepRec)));
             PF_CUDA(cudaMalloc(&bufA[k], px0 * sizeof(float2)));
             PF_CUDA(cudaMalloc(&bufB[k], px0 * sizeof(float2)));
-            PF_CUDA(cudaMalloc(&bufT[k], px0 * sizeof(float2)));
             PF_CUDA(cudaMalloc(&blurred[k], px0 * sizeof(float2)));
             PF_CUDA(cudaMalloc(&ratio[k], 256));
             PF_CUDA(cudaMalloc(&bnd[k], (p.bnd_lines + 1) * sizeof(uint4)));
@@ -195,8 +198,12 @@ struct pf_engine {
     int workspace(int idx, int rows, int cols, int pad, Workspace** out) {
         while ((int)pool.size() <= idx) pool.push_back(nullptr);
         Workspace* w = pool[idx];
-        if (w && (w->plan.rows != rows || w->plan.cols != cols || w->plan.pad != pad)) { delete w; w = nullptr; }
+        if (w && (w->plan.rows != rows || w->plan.cols != cols || w->plan.pad != pad)) {
+            std::lock_guard<std::mutex> cg(g_capture_mu);
+            delete w; w = nullptr; pool[idx] = nullptr;
+        }
         if (!w) {
+            std::lock_guard<std::mutex> cg(g_capture_mu);
             w = new Workspace();
             const int rc = w->init(rows, cols, pad);
             if (rc != PF_OK) { delete w; pool[idx] = nullptr; return rc; }
@@ -269,8 +276,6 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
             pf::launch_initial_flow(I0, I1, A0, A1, flow, w.ratio[d], h, wd, hint, e->search_dist, st);
             LAUNCHED(e->search_dist > 0 && hint != PF_HINT_UNKNOWN ? 2 : 1);
         }
-        pf::launch_blur15_rows(flow, w.bufT[d], h, wd, st);
-        pf::launch_blur15_cols(w.bufT[d], w.blurred[d], h, wd, nullptr, nullptr, nullptr, st);
         const float2* G0 = w.G[i0] + p.off[l];
         const float2* G1 = w.G[i1] + p.off[l];
         pf::Sweep2Args sa;
@@ -278,18 +283,19 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
         sa.G1s = w.Gs[i1] + p.skew_off[l];
         sa.s = p.skew[l];
         sa.g1s_last = (long long)pf::skew_elems(p.skew[l]) - 1;
-        sa.smem_ll = pf::sweep2_use_smem(wd) ? 1 : 0;
+        sa.smem_ll = 1;
+        // blur of the incoming flow (the sweeps regularise against it) + records of the forward sweep
+        pf::launch_blur15_prep(flow, w.blurred[d], h, wd, A0, A1, G0, G1, w.rec[d], +1, st);
         // forward sweep, in place on `flow`
-        pf::launch_sweep_prep(A0, A1, G0, G1, w.blurred[d], flow, w.rec[d], h, wd, +1, st);
         sa.flow = flow;
         sa.boundary = w.bnd[d] + p.bnd_off[2 * l];
         sa.ticket = w.tickets[d] + 2 * l;
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
         pf::launch_sweep2(sa, +1, st);
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
-        pf::launch_median5(flow, other, h, wd, st);
+        // median + records of the backward sweep
+        pf::launch_median5_prep(flow, other, w.blurred[d], h, wd, A0, A1, G0, G1, w.rec[d], -1, st);
         // backward sweep, in place on `other`
-        pf::launch_sweep_prep(A0, A1, G0, G1, w.blurred[d], other, w.rec[d], h, wd, -1, st);
         sa.flow = other;
         sa.boundary = w.bnd[d] + p.bnd_off[2 * l + 1];
         sa.ticket = w.tickets[d] + 2 * l + 1;
@@ -298,9 +304,8 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
         pf::launch_median5(other, flow, h, wd, st);
         // lowAlphaFlowDiffusion: blur + blend, written to `other`
-        pf::launch_blur15_rows(flow, w.bufT[d], h, wd, st);
-        pf::launch_blur15_cols(w.bufT[d], other, h, wd, A0, A1, flow, st);
-        LAUNCHED(10);
+        pf::launch_blur15_diffuse(flow, other, h, wd, A0, A1, st);
+        LAUNCHED(6);
         if (l > 0) {
             pf::launch_upsample_cubic(other, h, wd, flow, p.hs[l - 1], p.ws[l - 1], st);
             LAUNCHED(1);
@@ -365,7 +370,9 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
         if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], st, true)) != PF_OK) return rc;
         if ((rc = stage_input(w, 1, imgR, strideR, &dimg[1], &dstride[1], st, true)) != PF_OK) return rc;
         const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12);
-        if (w.graph_key != key) {
+        bool have_graph = w.graph_key == key;
+        if (!have_graph) {
+            std::lock_guard<std::mutex> cg(g_capture_mu);
             if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; w.graph_key = -1; }
             const uint64_t launched_before = g_launches.load();
             PF_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
@@ -374,21 +381,39 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
                 rc = enqueue_direction(e, w, d, d == 0 ? 0 : 1, hints[d], w.out[d], (size_t)w.plan.cols * sizeof(float2));
             if (rc == PF_OK && ndir == 2) {      // join direction 1 back into the capturing stream
                 if (cudaEventRecord(w.evDone[1], w.sDir[1]) != cudaSuccess || cudaStreamWaitEvent(st, w.evDone[1], 0) != cudaSuccess)
-                    rc = fail(PF_ERR_CUDA, "graph capture: join failed");
+                    rc = PF_ERR_CUDA;
             }
             cudaGraph_t g = nullptr;
-            const cudaError_t ce = cudaStreamEndCapture(st, &g);
-            if (rc != PF_OK) { if (g) cudaGraphDestroy(g); return rc; }
-            if (ce != cudaSuccess) return fail(PF_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
-            const cudaError_t ci = cudaGraphInstantiate(&w.graph, g, 0);
-            cudaGraphDestroy(g);
-            if (ci != cudaSuccess) return fail(PF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ci));
-            w.graph_key = key;
-            w.graph_launches = g_launches.load() - launched_before;   // kernels per replay
-            g_launches.store(launched_before);
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc == PF_OK && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&w.graph, g, 0);
+            if (g) cudaGraphDestroy(g);
+            const uint64_t captured = g_launches.load() - launched_before;
+            g_launches.fetch_sub(captured);
+            if (rc == PF_OK && ce == cudaSuccess && w.graph) {
+                w.graph_key = key;
+                w.graph_launches = captured;   // kernels per replay
+                have_graph = true;
+            } else {
+                // the capture was invalidated (e.g. a device-wide synchronisation issued by other code in the process):
+                // clear the error state and run this call with plain stream launches; capture is retried next call
+                cudaGetLastError();
+                if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
+                w.graph_key = -1;
+                g_err.clear();
+            }
         }
-        PF_CUDA(cudaGraphLaunch(w.graph, st));
-        LAUNCHED(w.graph_launches);
+        if (!have_graph) {
+            if ((rc = enqueue_shared(e, w, dimg, dstride)) != PF_OK) return rc;
+            for (int d = 0; d < ndir; ++d)
+                if ((rc = enqueue_direction(e, w, d, d == 0 ? 0 : 1, hints[d], w.out[d], (size_t)w.plan.cols * sizeof(float2))) != PF_OK) return rc;
+            if (ndir == 2) {
+                PF_CUDA(cudaEventRecord(w.evDone[1], w.sDir[1]));
+                PF_CUDA(cudaStreamWaitEvent(st, w.evDone[1], 0));
+            }
+        } else {
+            PF_CUDA(cudaGraphLaunch(w.graph, st));
+            LAUNCHED(w.graph_launches);
+        }
         for (int d = 0; d < ndir; ++d) {
             dflow[d] = w.out[d];
             dfstride[d] = (size_t)w.plan.cols * sizeof(float2);
@@ -465,8 +490,12 @@ int pf_engine_create(const char* name, int device, pf_engine** out) {
 void pf_engine_destroy(pf_engine* e) {
     if (!e) return;
     {
+        std::lock_guard<std::mutex> cg(g_capture_mu);
         DeviceGuard g(e->device);
-        cudaDeviceSynchronize();
+        for (Workspace* w : e->pool) {
+            if (!w) continue;
+            for (int d = 0; d < 2; ++d) if (w->sDir[d]) cudaStreamSynchronize(w->sDir[d]);
+        }
         delete e;
     }
 }
@@ -590,7 +619,7 @@ static int combine_impl(pf_engine* e, Workspace* w, cudaStream_t st, const uint8
     size_t dsB;
     if (is_device_ptr(blend)) { dB = (const float*)blend; dsB = sB; }
     else {
-        if (!w->blend) PF_CUDA(cudaMalloc(&w->blend, (size_t)rows * cols * 4));
+        if (!w->blend) { std::lock_guard<std::mutex> cg(g_capture_mu); PF_CUDA(cudaMalloc(&w->blend, (size_t)rows * cols * 4)); }
         PF_CUDA(cudaMemcpy2DAsync(w->blend, (size_t)cols * 4, blend, sB, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, st));
         dB = w->blend; dsB = (size_t)cols * 4;
     }
@@ -599,7 +628,7 @@ static int combine_impl(pf_engine* e, Workspace* w, cudaStream_t st, const uint8
     size_t dsO;
     if (dev_out) { dO = (uint8_t*)out; dsO = sOut; }
     else {
-        if (!w->merged) PF_CUDA(cudaMalloc(&w->merged, (size_t)rows * cols * 4));
+        if (!w->merged) { std::lock_guard<std::mutex> cg(g_capture_mu); PF_CUDA(cudaMalloc(&w->merged, (size_t)rows * cols * 4)); }
         dO = w->merged; dsO = (size_t)cols * 4;
     }
     pf::launch_combine(dL, sL, dR, sR, dLR, sLR, dRL, sRL, dB, dsB, rows, cols, dO, dsO, st);
@@ -696,8 +725,8 @@ int pf_host_free(void* p) {
 namespace {
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    int alloc(size_t n) { PF_CUDA(cudaMalloc(&p, n ? n : 1)); return PF_OK; }
+    ~DevBuf() { std::lock_guard<std::mutex> cg(g_capture_mu); cudaFree(p); }
+    int alloc(size_t n) { std::lock_guard<std::mutex> cg(g_capture_mu); PF_CUDA(cudaMalloc(&p, n ? n : 1)); return PF_OK; }
     int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; PF_CUDA(cudaMemcpy(p, h, n, cudaMemcpyHostToDevice)); return PF_OK; }
     int download(void* h, size_t n) { PF_CUDA(cudaDeviceSynchronize()); PF_CUDA(cudaGetLastError()); PF_CUDA(cudaMemcpy(h, p, n, cudaMemcpyDeviceToHost)); return PF_OK; }
     template <class T> T* as() { return (T*)p; }
@@ -741,14 +770,16 @@ int pf_stage_gradient(const float* I, float* G, int h, int w) {
     return d.download(G, (size_t)h * w * 8);
 }
 int pf_stage_blur15(const float* flow, float* dst, int h, int w, const float* alpha0, const float* alpha1) {
-    DevBuf s, t, d, a0, a1;
+    DevBuf s, d, a0, a1;
     const size_t n = (size_t)h * w * 8;
-    RC(s.upload(flow, n)); RC(t.alloc(n)); RC(d.alloc(n));
-    if (alpha0) { RC(a0.upload(alpha0, n / 2)); RC(a1.upload(alpha1, n / 2)); }
-    pf::launch_blur15_rows(s.as<float2>(), t.as<float2>(), h, w, 0);
-    pf::launch_blur15_cols(t.as<float2>(), d.as<float2>(), h, w, alpha0 ? a0.as<float>() : nullptr, alpha0 ? a1.as<float>() : nullptr,
-                           s.as<float2>(), 0);
-    LAUNCHED(2);
+    RC(s.upload(flow, n)); RC(d.alloc(n));
+    if (alpha0) {
+        RC(a0.upload(alpha0, n / 2)); RC(a1.upload(alpha1, n / 2));
+        pf::launch_blur15_diffuse(s.as<float2>(), d.as<float2>(), h, w, a0.as<float>(), a1.as<float>(), 0);
+    } else {
+        pf::launch_blur15(s.as<float2>(), d.as<float2>(), h, w, 0);
+    }
+    LAUNCHED(1);
     return d.download(dst, n);
 }
 int pf_stage_median5(const float* flow, float* dst, int h, int w) {

@@ -1,0 +1,157 @@
+// pf_fused.cu -- shared-memory-tiled, fused stencil kernels of one pyramid level (CPU/PixFlow.hpp:272-340).
+//
+// Per level and direction the reference runs: 15x15 blur of the flow (:307), forward sweep, median5 (:325), backward
+// sweep, median5 (:338), 15x15 blur + alpha blend (:339, :388-405).  Around the two sweep kernels (pf_sweep.cu) that is
+// done here in four launches instead of eight, each reading its input tile once:
+//   k_blur15<PREP>     flow -> [rows pass -> cols pass in shared memory] -> blurred  (+ the forward sweep's records)
+//   k_median5<PREP>    flow -> 5x5 median from a shared-memory tile                  (+ the backward sweep's records)
+//   k_median5<NONE>    plain median
+//   k_blur15<DIFFUSE>  flow -> blur -> lowAlphaFlowDiffusion blend
+// Arithmetic is unchanged (same taps, same order of the separately rounded fp32 operations as the two-pass versions):
+// the row pass of a reflected row equals the row pass computed at that row, so building the halo with reflect-101 /
+// replicate indices at load time reproduces OpenCV's border handling exactly.
+#include "pf_kernels.cuh"
+#include "pf_math.cuh"
+#include "pf_prep.cuh"
+
+namespace pf {
+
+namespace {
+
+// One output pixel per thread: most launches are small pyramid levels whose duration is the latency of one thread.
+constexpr int TILE = 32;                 // tile width
+constexpr int BTH = 16;                  // blur tile height (512 threads)
+constexpr int BR = 7;                    // radius of the 15-tap Gaussian
+constexpr int BW = TILE + 2 * BR;        // 46
+constexpr int BH = BTH + 2 * BR;         // 30
+constexpr int MTH = 8;                   // median tile height (256 threads)
+constexpr int MR = 2;                    // radius of the 5x5 median
+constexpr int MW = TILE + 2 * MR;        // 36
+constexpr int MH = MTH + 2 * MR;         // 12
+
+enum { MODE_PLAIN = 0, MODE_PREP = 1, MODE_DIFFUSE = 2 };
+
+// 15x15 sigma 8 Gaussian of the 2-channel flow: row pass left-to-right over the 15 taps, column pass in the symmetric
+// form, both from shared memory.
+template <int MODE>
+__global__ void __launch_bounds__(TILE * BTH)
+k_blur15(const float2* __restrict__ flow, float2* __restrict__ out, int h, int w, PrepArgs pa) {
+    PF_GAUSS_TABLES
+    __shared__ float2 s_in[BH][BW];          // flow tile + halo, reflect-101 at the image border
+    __shared__ float2 s_row[BH][TILE];       // row pass
+    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * BTH;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * TILE + tx;
+    for (int e = tid; e < BH * BW; e += TILE * BTH) {
+        const int ly = e / BW, lx = e - ly * BW;
+        const int gy = reflect101(y0 - BR + ly, h), gx = reflect101(x0 - BR + lx, w);
+        s_in[ly][lx] = flow[(size_t)gy * w + gx];
+    }
+    __syncthreads();
+    for (int ly = ty; ly < BH; ly += BTH) {
+        float2 v = s_in[ly][tx];
+        float sx = fmul(kG15[7], v.x), sy = fmul(kG15[7], v.y);
+#pragma unroll
+        for (int i = 1; i < 15; ++i) {
+            v = s_in[ly][tx + i];
+            const float k = kG15[i < 7 ? 7 - i : i - 7];
+            sx = fadd(sx, fmul(k, v.x));
+            sy = fadd(sy, fmul(k, v.y));
+        }
+        s_row[ly][tx] = make_float2(sx, sy);
+    }
+    __syncthreads();
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= w || y >= h) return;
+    const float2 cen = s_row[ty + BR][tx];
+    float sx = fmul(kG15[0], cen.x), sy = fmul(kG15[0], cen.y);
+#pragma unroll
+    for (int i = 1; i <= 7; ++i) {
+        const float2 a = s_row[ty + BR + i][tx], b = s_row[ty + BR - i][tx];
+        sx = fadd(sx, fmul(kG15[i], fadd(a.x, b.x)));
+        sy = fadd(sy, fmul(kG15[i], fadd(a.y, b.y)));
+    }
+    const size_t p = (size_t)y * w + x;
+    const float2 f = s_in[ty + BR][tx + BR];
+    if (MODE == MODE_DIFFUSE) {          // lowAlphaFlowDiffusion, CPU/PixFlow.hpp:395-404
+        const float d = fsub(1.0f, fmul(pa.alpha0[p], pa.alpha1[p]));
+        const float e = fsub(1.0f, d);
+        out[p] = make_float2(fadd(fmul(d, sx), fmul(e, f.x)), fadd(fmul(d, sy), fmul(e, f.y)));
+    } else {
+        out[p] = make_float2(sx, sy);
+        if (MODE == MODE_PREP) emit_record(pa, make_err_ctx(pa.G1, w, h), x, y, w, h, f, make_float2(sx, sy));
+    }
+    (void)kG5; (void)kG3O; (void)kG3H;
+}
+
+// medianBlur(32FC2, 5), replicate border, from a shared-memory tile (+ the records of the coming sweep)
+template <int MODE>
+__global__ void __launch_bounds__(TILE * MTH)
+k_median5(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ blurred, int h, int w, PrepArgs pa) {
+    __shared__ float2 s_in[MH][MW + 1];
+    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * MTH;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * TILE + tx;
+    for (int e = tid; e < MH * MW; e += TILE * MTH) {
+        const int ly = e / MW, lx = e - ly * MW;
+        const int gy = clampi(y0 - MR + ly, 0, h - 1), gx = clampi(x0 - MR + lx, 0, w - 1);
+        s_in[ly][lx] = src[(size_t)gy * w + gx];
+    }
+    __syncthreads();
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= w || y >= h) return;
+    float vx[25], vy[25];
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            const float2 v = s_in[ty + dy][tx + dx];
+            vx[dy * 5 + dx] = v.x;
+            vy[dy * 5 + dx] = v.y;
+        }
+    const float2 m = make_float2(median25(vx), median25(vy));
+    const size_t p = (size_t)y * w + x;
+    dst[p] = m;
+    if (MODE == MODE_PREP) emit_record(pa, make_err_ctx(pa.G1, w, h), x, y, w, h, m, blurred[p]);
+}
+
+inline dim3 blur_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + BTH - 1) / BTH); }
+inline dim3 median_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + MTH - 1) / MTH); }
+
+PrepArgs make_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir) {
+    PrepArgs pa;
+    pa.alpha0 = alpha0; pa.alpha1 = alpha1; pa.G0 = G0; pa.G1 = G1; pa.rec = rec;
+    pa.R = 32 / sweep_lanes_per_row();
+    pa.dir = dir;
+    return pa;
+}
+
+}  // namespace
+
+void launch_blur15(const float2* flow, float2* blurred, int h, int w, cudaStream_t st) {
+    PrepArgs pa = {};
+    k_blur15<MODE_PLAIN><<<blur_grid(w, h), dim3(TILE, BTH), 0, st>>>(flow, blurred, h, w, pa);
+}
+
+void launch_blur15_prep(const float2* flow, float2* blurred, int h, int w, const float* alpha0, const float* alpha1,
+                        const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
+    k_blur15<MODE_PREP><<<blur_grid(w, h), dim3(TILE, BTH), 0, st>>>(flow, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir));
+}
+
+void launch_blur15_diffuse(const float2* flow, float2* out, int h, int w, const float* alpha0, const float* alpha1, cudaStream_t st) {
+    PrepArgs pa = {};
+    pa.alpha0 = alpha0; pa.alpha1 = alpha1;
+    k_blur15<MODE_DIFFUSE><<<blur_grid(w, h), dim3(TILE, BTH), 0, st>>>(flow, out, h, w, pa);
+}
+
+void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st) {
+    PrepArgs pa = {};
+    k_median5<MODE_PLAIN><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, nullptr, h, w, pa);
+}
+
+void launch_median5_prep(const float2* src, float2* dst, const float2* blurred, int h, int w, const float* alpha0,
+                         const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
+    k_median5<MODE_PREP><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir));
+}
+
+}  // namespace pf

@@ -195,100 +195,6 @@ void launch_gradient(const float* I, float2* G, int h, int w, cudaStream_t st) {
 }
 
 // ====================================================================================================
-// 15x15 sigma 8 blur on float2 (row pass: left-to-right taps; column pass: symmetric form)
-// ====================================================================================================
-__global__ void __launch_bounds__(256)
-k_blur15_rows(const float2* __restrict__ src, float2* __restrict__ tmp, int h, int w) {
-    PF_GAUSS_TABLES
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const float2* S = src + (size_t)y * w;
-    float2 v = S[reflect101(x - 7, w)];
-    float sx = fmul(kG15[7], v.x), sy = fmul(kG15[7], v.y);
-#pragma unroll
-    for (int i = 1; i < 15; ++i) {
-        v = S[reflect101(x - 7 + i, w)];
-        const float k = kG15[i < 7 ? 7 - i : i - 7];
-        sx = fadd(sx, fmul(k, v.x));
-        sy = fadd(sy, fmul(k, v.y));
-    }
-    tmp[(size_t)y * w + x] = make_float2(sx, sy);
-    (void)kG5; (void)kG3O; (void)kG3H;
-}
-
-template <bool DIFFUSE>
-__global__ void __launch_bounds__(256)
-k_blur15_cols(const float2* __restrict__ tmp, float2* __restrict__ dst, int h, int w,
-              const float* __restrict__ alpha0, const float* __restrict__ alpha1, const float2* __restrict__ flow) {
-    PF_GAUSS_TABLES
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    float2 c = tmp[(size_t)y * w + x];
-    float sx = fmul(kG15[0], c.x), sy = fmul(kG15[0], c.y);
-#pragma unroll
-    for (int i = 1; i <= 7; ++i) {
-        const float2 a = tmp[(size_t)reflect101(y + i, h) * w + x];
-        const float2 b = tmp[(size_t)reflect101(y - i, h) * w + x];
-        sx = fadd(sx, fmul(kG15[i], fadd(a.x, b.x)));
-        sy = fadd(sy, fmul(kG15[i], fadd(a.y, b.y)));
-    }
-    if (DIFFUSE) {   // lowAlphaFlowDiffusion, CPU/PixFlow.hpp:395-404
-        const size_t p = (size_t)y * w + x;
-        const float d = fsub(1.0f, fmul(alpha0[p], alpha1[p]));
-        const float e = fsub(1.0f, d);
-        const float2 f = flow[p];
-        sx = fadd(fmul(d, sx), fmul(e, f.x));
-        sy = fadd(fmul(d, sy), fmul(e, f.y));
-    }
-    dst[(size_t)y * w + x] = make_float2(sx, sy);
-    (void)kG5; (void)kG3O; (void)kG3H;
-}
-
-void launch_blur15_rows(const float2* src, float2* tmp, int h, int w, cudaStream_t st) {
-    dim3 b(32, 8);
-    k_blur15_rows<<<grid2d(w, h, b), b, 0, st>>>(src, tmp, h, w);
-}
-
-void launch_blur15_cols(const float2* tmp, float2* dst, int h, int w,
-                        const float* alpha0, const float* alpha1, const float2* flow, cudaStream_t st) {
-    dim3 b(32, 8);
-    if (alpha0) k_blur15_cols<true><<<grid2d(w, h, b), b, 0, st>>>(tmp, dst, h, w, alpha0, alpha1, flow);
-    else k_blur15_cols<false><<<grid2d(w, h, b), b, 0, st>>>(tmp, dst, h, w, nullptr, nullptr, nullptr);
-}
-
-// ====================================================================================================
-// median 5x5 on float2 (replicate border)
-// ====================================================================================================
-__global__ void __launch_bounds__(128)
-k_median5(const float2* __restrict__ src, float2* __restrict__ dst, int h, int w) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    float vx[25], vy[25];
-    int xs[5];
-#pragma unroll
-    for (int d = 0; d < 5; ++d) xs[d] = clampi(x + d - 2, 0, w - 1);
-#pragma unroll
-    for (int dy = 0; dy < 5; ++dy) {
-        const float2* S = src + (size_t)clampi(y + dy - 2, 0, h - 1) * w;
-#pragma unroll
-        for (int dx = 0; dx < 5; ++dx) {
-            const float2 v = S[xs[dx]];
-            vx[dy * 5 + dx] = v.x;
-            vy[dy * 5 + dx] = v.y;
-        }
-    }
-    dst[(size_t)y * w + x] = make_float2(median25(vx), median25(vy));
-}
-
-void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st) {
-    dim3 b(32, 4);
-    k_median5<<<grid2d(w, h, b), b, 0, st>>>(src, dst, h, w);
-}
-
-// ====================================================================================================
 // inter-level upsample: INTER_CUBIC on float2, then * (1/0.9)
 // ====================================================================================================
 __global__ void __launch_bounds__(256)

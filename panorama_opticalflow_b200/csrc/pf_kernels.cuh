@@ -23,15 +23,6 @@ void launch_pyr_down(const PlaneSet& ps, int nplanes, int sh, int sw, int dh, in
 // ---- gradients (CPU/PixFlow.hpp:284-294): Sobel k=1 (replicate) + 3x3 sigma 0.5 blur, interleaved out --
 void launch_gradient(const float* I, float2* G, int h, int w, cudaStream_t st);
 
-// ---- 15x15 sigma 8 blur of the 2-channel flow (CPU/PixFlow.hpp:307, :390) ----------------------------
-void launch_blur15_rows(const float2* src, float2* tmp, int h, int w, cudaStream_t st);
-// column pass; if alpha0 != nullptr fuses lowAlphaFlowDiffusion (CPU/PixFlow.hpp:395-404) with `flow`
-void launch_blur15_cols(const float2* tmp, float2* dst, int h, int w,
-                        const float* alpha0, const float* alpha1, const float2* flow, cudaStream_t st);
-
-// ---- medianBlur(32FC2, 5) (CPU/PixFlow.hpp:325, :338) ------------------------------------------------
-void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st);
-
 // ---- Gauss-Seidel sweeps as an exact anti-diagonal wavefront (CPU/PixFlow.hpp:315-337), pf_sweep.cu ------
 // Skewed (anti-diagonal-major) layout: element (x,y) at (x+y)*pitch + (posx ? x : y)
 struct Skew { int w, h, pitch, posx; };
@@ -46,6 +37,18 @@ int sweep_lanes_per_row();                // 2 (default), 8 or 1; env PF_SWEEP_L
 size_t sweep_rec_count(int h, int w);     // SweepRec elements a (h x w) level needs
 void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
                        const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st);
+
+// ---- fused, shared-memory-tiled stencils of one level (pf_fused.cu) -----------------------------------------------
+// 15x15 sigma 8 blur of the 2-channel flow (CPU/PixFlow.hpp:307): plain, with the forward sweep's records fused in,
+// or with lowAlphaFlowDiffusion (CPU/PixFlow.hpp:388-405) fused in
+void launch_blur15(const float2* flow, float2* blurred, int h, int w, cudaStream_t st);
+void launch_blur15_prep(const float2* flow, float2* blurred, int h, int w, const float* alpha0, const float* alpha1,
+                        const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st);
+void launch_blur15_diffuse(const float2* flow, float2* out, int h, int w, const float* alpha0, const float* alpha1, cudaStream_t st);
+// medianBlur(32FC2, 5) (CPU/PixFlow.hpp:325, :338): plain, or with the backward sweep's records fused in
+void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st);
+void launch_median5_prep(const float2* src, float2* dst, const float2* blurred, int h, int w, const float* alpha0,
+                         const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st);
 struct Sweep2Args {
     const SweepRec* rec;                      // wavefront-packed records from launch_sweep_prep (same dir)
     const float2* G1s;                        // skewed gradients of image 1

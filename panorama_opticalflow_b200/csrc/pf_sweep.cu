@@ -40,6 +40,7 @@
 
 #include "pf_kernels.cuh"
 #include "pf_math.cuh"
+#include "pf_prep.cuh"
 
 namespace pf {
 
@@ -113,45 +114,25 @@ size_t sweep_rec_count(int h, int w) {
     return best;
 }
 
-template <int DIR>
+// stand-alone form (the production path fuses this into the blur / median kernels, pf_fused.cu)
 __global__ void __launch_bounds__(256)
-k_sweep_prep(const float* __restrict__ alpha0, const float* __restrict__ alpha1, const float2* __restrict__ G0,
-             const float2* __restrict__ G1, const float2* __restrict__ blurred, const float2* __restrict__ flow,
-             SweepRec* __restrict__ rec, int h, int w, int R) {
+k_sweep_prep(const float2* __restrict__ blurred, const float2* __restrict__ flow, int h, int w, PrepArgs pa) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
-    ErrCtx c;
-    c.G1 = G1; c.w = w; c.h = h;
-    c.wm2 = fsub((float)w, 2.0f); c.hm2 = fsub((float)h, 2.0f); c.fw = (float)w;
+    const ErrCtx c = make_err_ctx(pa.G1, w, h);
     const size_t p = (size_t)y * w + x;
-    const float2 f = flow[p];
-    const float2 g0 = G0[p];
-    const float2 bl = blurred[p];
-    float4 A = make_float4(__int_as_float(0xff800000), f.x, f.y, 0.0f);   // {-inf, f0}: never updated
-    if (alpha0[p] > PF_ALPHA_THRESHOLD && alpha1[p] > PF_ALPHA_THRESHOLD) {
-        const float e0 = error_function(c, x, y, g0, bl, f.x, f.y);
-        const float ex = error_function(c, x, y, g0, bl, fadd(f.x, PF_GRAD_EPS), fadd(f.y, 0.0f));
-        const float ey = error_function(c, x, y, g0, bl, fadd(f.x, 0.0f), fadd(f.y, PF_GRAD_EPS));
-        A.x = e0;
-        A.y = fsub(f.x, fmul(PF_GRAD_STEP, __fdiv_rn(fsub(ex, e0), PF_GRAD_EPS)));
-        A.z = fsub(f.y, fmul(PF_GRAD_STEP, __fdiv_rn(fsub(ey, e0), PF_GRAD_EPS)));
-    }
-    const int j = DIR > 0 ? y : h - 1 - y, i = DIR > 0 ? x : w - 1 - x;
-    const int wb = j / R, g = j % R;
-    const size_t idx = ((size_t)wb * (w + R - 1) + (i + g)) * R + g;
-    SweepRec r;
-    r.a = A;
-    r.b = make_float4(g0.x, g0.y, bl.x, bl.y);
-    rec[idx] = r;
+    emit_record(pa, c, x, y, w, h, flow[p], blurred[p]);
 }
 
 void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
                        const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st) {
     dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
-    const int R = 32 / sweep_lanes_per_row();
-    if (dir > 0) k_sweep_prep<1><<<g, b, 0, st>>>(alpha0, alpha1, G0, G1, blurred, flow, rec, h, w, R);
-    else k_sweep_prep<-1><<<g, b, 0, st>>>(alpha0, alpha1, G0, G1, blurred, flow, rec, h, w, R);
+    PrepArgs pa;
+    pa.alpha0 = alpha0; pa.alpha1 = alpha1; pa.G0 = G0; pa.G1 = G1; pa.rec = rec;
+    pa.R = 32 / sweep_lanes_per_row();
+    pa.dir = dir;
+    k_sweep_prep<<<g, b, 0, st>>>(blurred, flow, h, w, pa);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -246,7 +227,9 @@ __device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float y
         // cp.async.ca into a scratch slot allocates the line in L1 and never blocks (its data is not used)
         int pi = gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
         pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
+#ifndef PF_EXP_NOTOUCH
         cp_async16(k.touch, k.G1s + pi);
+#endif
     }
     float g1x, g1y;
     {
@@ -496,7 +479,11 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
         res.y = valid ? out.y : res.y;
         // ---- results: flow (row-major, only where alpha > 0.9) and the hand-off of the warp's last row ----
         const int x = DIR > 0 ? i : w - 1 - i;
+#ifndef PF_EXP_NOSTORE
         if (active && sub == 0) flow_row[x] = out;
+#else
+        if (active && sub == 0 && out.x == 12345.678f) flow_row[x] = out;
+#endif
         const int i_last = s - (G::ROWS - 1);                 // column of the warp's last row (warp-uniform)
         if (ring_out && i_last >= out_limit)                  // back-pressure, rare: wait until the slot is free
             while (i_last >= out_limit) out_limit = ld_volatile_shared_s32(prog_out) + SW_LL_RING;
@@ -612,6 +599,9 @@ static void launch_sweep_p(const Sweep2Args& a, int dir, cudaStream_t st) {
 
 void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st) {
     (void)rows_per_cta;
+    static int skip = -1;
+    if (skip < 0) skip = getenv("PF_EXP_SKIP_SWEEP") ? 1 : 0;    // timing experiment only: results are wrong
+    if (skip) return;
     switch (sweep_lanes_per_row()) {
     case 1: launch_sweep_p<1>(a, dir, st); break;
     case 2: launch_sweep_p<2>(a, dir, st); break;
