@@ -21,6 +21,67 @@ __device__ __forceinline__ ErrCtx make_err_ctx(const float2* G1, int w, int h) {
     return c;
 }
 
+// ---- errorFunction at the three probes f, f+(eps,0), f+(0,eps) of one pixel (CPU/PixFlow.hpp:318, :382-383) ----------
+// The probes almost always fall into the same bilinear cell, so the four gradient texels are fetched once and only
+// re-fetched when a probe crosses a cell boundary; the IEEE divisions and square roots use the branch-free exactly
+// rounded sequences of pf_math.cuh, with a per-thread fallback to the intrinsics outside their validity range.
+struct BilCell { int x0, y0; float xR, yR; };
+
+__device__ __forceinline__ BilCell bil_cell_rm(const ErrCtx& c, float x, float y) {
+    { const float t = (0.0f < x) ? x : 0.0f; x = (t < c.wm2) ? t : c.wm2; }     // getPixBilinear32FExtend, :409-410
+    { const float t = (0.0f < y) ? y : 0.0f; y = (t < c.hm2) ? t : c.hm2; }
+    BilCell b;
+    b.x0 = __float2int_rz(x); b.y0 = __float2int_rz(y);
+    b.xR = fsub(x, (float)b.x0); b.yR = fsub(y, (float)b.y0);
+    return b;
+}
+
+struct Texels { float2 f00, f10, f01, f11; };
+
+__device__ __forceinline__ Texels load_texels_rm(const ErrCtx& c, int x0, int y0) {
+    const float2* p = c.G1 + (size_t)y0 * c.w + x0;
+    Texels t;
+    t.f00 = __ldg(p); t.f10 = __ldg(p + 1); t.f01 = __ldg(p + c.w); t.f11 = __ldg(p + c.w + 1);
+    return t;
+}
+
+__device__ __forceinline__ float2 bil_interp(const Texels& t, float xR, float yR) {      // :415-424, both planes
+    float2 r;
+    {
+        const float a2 = fsub(t.f10.x, t.f00.x), a3 = fsub(t.f01.x, t.f00.x);
+        const float a4 = fsub(fsub(fadd(t.f00.x, t.f11.x), t.f10.x), t.f01.x);
+        r.x = fadd(fadd(fadd(t.f00.x, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
+    }
+    {
+        const float a2 = fsub(t.f10.y, t.f00.y), a3 = fsub(t.f01.y, t.f00.y);
+        const float a4 = fsub(fsub(fadd(t.f00.y, t.f11.y), t.f10.y), t.f01.y);
+        r.y = fadd(fadd(fadd(t.f00.y, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
+    }
+    return r;
+}
+
+template <bool SLOW>
+__device__ __forceinline__ float err_from_g1(const ErrCtx& c, float rcp_w, float2 g0, float2 bl, float2 g1, float fx, float fy, bool& bad) {
+    const float dX = fsub(bl.x, fx), dY = fsub(bl.y, fy);
+    const float ss = fadd(fmul(dX, dX), fmul(dY, dY));
+    const float ex = fsub(g0.x, g1.x), ey = fsub(g0.y, g1.y);
+    const float gs = fadd(fmul(ex, ex), fmul(ey, ey));
+    const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
+    float smooth, grad, ry, rx;
+    if (SLOW) {
+        smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
+        ry = __fdiv_rn(ty, c.fw); rx = __fdiv_rn(tx, c.fw);
+    } else {
+        smooth = sqrt_exact_fast(ss); grad = sqrt_exact_fast(gs);
+        ry = div_by_const(ty, c.fw, rcp_w); rx = div_by_const(tx, c.fw, rcp_w);
+        bad = bad || !(in_sqrt_range(ss) && in_sqrt_range(gs) && in_div_range(ty) && in_div_range(tx));
+    }
+    float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
+    err = fadd(err, ry);
+    err = fadd(err, rx);
+    return err;
+}
+
 // Record {E(f0), r0.x, r0.y, - | I0x, I0y, blur.x, blur.y} of pixel (x,y) with old flow f and blurred flow bl
 // (CPU/PixFlow.hpp:318 currErr, :321 + :364-386 the gradient step taken when no proposal wins); pixels that the sweep
 // must not update (alpha <= 0.9, :317) get {-inf, f}.  Stored in the wavefront-packed order of the sweep kernel:
@@ -30,12 +91,36 @@ __device__ __forceinline__ void emit_record(const PrepArgs& a, const ErrCtx& c, 
     const float2 g0 = a.G0[p];
     float4 A = make_float4(__int_as_float(0xff800000), f.x, f.y, 0.0f);
     if (a.alpha0[p] > PF_ALPHA_THRESHOLD && a.alpha1[p] > PF_ALPHA_THRESHOLD) {
-        const float e0 = error_function(c, x, y, g0, bl, f.x, f.y);
-        const float ex = error_function(c, x, y, g0, bl, fadd(f.x, PF_GRAD_EPS), fadd(f.y, 0.0f));
-        const float ey = error_function(c, x, y, g0, bl, fadd(f.x, 0.0f), fadd(f.y, PF_GRAD_EPS));
+        const float xf = (float)x, yf = (float)y;
+        const float fx1 = fadd(f.x, PF_GRAD_EPS), fy1 = fadd(f.y, 0.0f);
+        const float fx2 = fadd(f.x, 0.0f), fy2 = fadd(f.y, PF_GRAD_EPS);
+        const BilCell c0 = bil_cell_rm(c, fadd(xf, f.x), fadd(yf, f.y));
+        const BilCell c1 = bil_cell_rm(c, fadd(xf, fx1), fadd(yf, fy1));
+        const BilCell c2 = bil_cell_rm(c, fadd(xf, fx2), fadd(yf, fy2));
+        const Texels t0 = load_texels_rm(c, c0.x0, c0.y0);
+        Texels t1 = t0, t2 = t0;
+        if (c1.x0 != c0.x0 || c1.y0 != c0.y0) t1 = load_texels_rm(c, c1.x0, c1.y0);    // probe crossed a cell boundary
+        if (c2.x0 != c0.x0 || c2.y0 != c0.y0) t2 = load_texels_rm(c, c2.x0, c2.y0);
+        const float2 g1a = bil_interp(t0, c0.xR, c0.yR), g1b = bil_interp(t1, c1.xR, c1.yR), g1c = bil_interp(t2, c2.xR, c2.yR);
+        const float rcp_w = __frcp_rn(c.fw), rcp_eps = __frcp_rn(PF_GRAD_EPS);
+        bool bad = false;
+        float e0 = err_from_g1<false>(c, rcp_w, g0, bl, g1a, f.x, f.y, bad);
+        float ex = err_from_g1<false>(c, rcp_w, g0, bl, g1b, fx1, fy1, bad);
+        float ey = err_from_g1<false>(c, rcp_w, g0, bl, g1c, fx2, fy2, bad);
+        float dx = fsub(ex, e0), dy = fsub(ey, e0);
+        float qx = div_by_const(dx, PF_GRAD_EPS, rcp_eps), qy = div_by_const(dy, PF_GRAD_EPS, rcp_eps);
+        bad = bad || !(in_div_range(dx) && in_div_range(dy));
+        if (bad) {                                   // rare: operands outside the verified range -> IEEE intrinsics
+            bool dummy = false;
+            e0 = err_from_g1<true>(c, rcp_w, g0, bl, g1a, f.x, f.y, dummy);
+            ex = err_from_g1<true>(c, rcp_w, g0, bl, g1b, fx1, fy1, dummy);
+            ey = err_from_g1<true>(c, rcp_w, g0, bl, g1c, fx2, fy2, dummy);
+            qx = __fdiv_rn(fsub(ex, e0), PF_GRAD_EPS);
+            qy = __fdiv_rn(fsub(ey, e0), PF_GRAD_EPS);
+        }
         A.x = e0;
-        A.y = fsub(f.x, fmul(PF_GRAD_STEP, __fdiv_rn(fsub(ex, e0), PF_GRAD_EPS)));
-        A.z = fsub(f.y, fmul(PF_GRAD_STEP, __fdiv_rn(fsub(ey, e0), PF_GRAD_EPS)));
+        A.y = fsub(f.x, fmul(PF_GRAD_STEP, qx));
+        A.z = fsub(f.y, fmul(PF_GRAD_STEP, qy));
     }
     const int j = a.dir > 0 ? y : h - 1 - y, i = a.dir > 0 ? x : w - 1 - x;
     const int wb = j / a.R, g = j % a.R;
