@@ -6,35 +6,38 @@
 // array being written.  Any order that respects those two dependencies gives bit-identical results, and the
 // anti-diagonal order is the one with the shortest critical path (w+h-1 steps).
 //
-// Data layout ("skewed", anti-diagonal-major): element (x,y) lives at (x+y)*pitch + pos, pos = x if w<=h else y.
-// All pixels a warp touches in one wavefront step sit on one anti-diagonal, i.e. in ONE contiguous run of memory:
-// every per-step load of the sweep is coalesced (1-2 cache lines) instead of one line per row.  The same holds
-// for the bilinear gathers of the I1 gradients as long as neighbouring rows have similar flow.
+// Data layouts:
+//   * gradients of image 1 ("skewed", anti-diagonal-major): element (x,y) at (x+y)*pitch + pos, pos = x if w<=h else y.
+//     All pixels a warp touches in one wavefront step sit on one anti-diagonal, so the bilinear gathers of a step are
+//     coalesced (1-2 cache lines per tap) as long as neighbouring rows have similar flow, instead of one line per row.
+//   * per-pixel records ("wavefront-packed", written by the prep code fused into the stencil kernels, pf_prep.cuh):
+//     one contiguous run of R*32 bytes per warp-step, consumed strictly sequentially -> staged through a shared-memory
+//     ring with cp.async several steps ahead, so the step never waits on L2/HBM.
 //
 // Work split per pixel (i,j):
 //   * everything that depends only on the pixel's OWN old flow f0 -- E(f0), E(f0+dx), E(f0+dy) and the result
-//     r0 = f0 - step*grad(f0) that is kept when no neighbour proposal wins -- is hoisted into k_sweep_prep,
-//     a fully parallel kernel (record A = {E(f0), r0.x, r0.y}; inactive pixels get {-inf, f0});
-//   * the sweep kernel proper only evaluates the two neighbour candidates, speculatively and in parallel: eight
-//     lanes per row, lanes 0-2 take the left candidate (the row's own previous result) at offsets (0,0), (eps,0),
-//     (0,eps), lanes 3-5 the up candidate (previous result of the row above, one shuffle away) at the same three
-//     offsets -- ONE error evaluation per lane, so the dependent instruction chain of a step is one evaluation
-//     long.  Six shuffles hand every lane of the row all six errors; each lane then finishes both candidates'
-//     gradient steps and does the two compares.  Critical path per step: shuffle, bilinear gather, one error
-//     evaluation, shuffle, one division, two compares (measured: see profiles/).
+//     r0 = f0 - step*grad(f0) that is kept when no neighbour proposal wins -- is hoisted out of the dependency chain
+//     into the fully parallel prep (record a = {E(f0), r0.x, r0.y}; pixels that must not be updated get {-inf, f0});
+//   * the sweep kernel only evaluates the two neighbour candidates -- left (the row's own previous result) and up
+//     (previous result of the row above, one shuffle away) -- speculatively at the three probe offsets (0,0), (eps,0),
+//     (0,eps) each, finishes BOTH candidates' gradient steps and then does the reference's two compares.
+//     P lanes per row (template): P = 2 (default) one candidate per lane, three probes sharing one texel gather;
+//     P = 8 one probe per lane (six shuffles collect the errors); P = 1 both candidates on one lane.
 //   * the step body is branch-free: the IEEE divisions (by eps and by cols, both loop-invariant) and square roots
 //     use exactly-rounded branchless sequences (pf_math.cuh, verified exhaustively on the GPU); a warp-uniform
 //     vote redoes the step with the IEEE intrinsics in the rare case an operand leaves their validity range.
-//   * 4 rows per warp, 8 compute warps (32 rows) per CTA.  Warps hand the last row's results to the next warp
-//     through LL-style lines {fx, flag, fy, flag} (16-byte single-instruction stores, each 8-byte half
-//     self-validating, no fences, so L1 is never invalidated) in shared memory inside a CTA and in global memory
-//     between CTAs; a ninth "poller" warp per CTA spins on the upstream CTA's global lines and forwards them into
-//     shared memory, so no compute warp ever waits on an L2 round trip.  The shared-memory lines are 64-entry rings
-//     (flag = lap number, back-pressure through a progress counter), so a CTA needs < 32 KB of shared memory and
-//     several sweeps (both directions, several pairs) are co-resident on an SM -- the step is latency-bound on
-//     one warp, so throughput comes from interleaving independent wavefronts on the same schedulers.  CTAs take
-//     their row block from an atomic ticket, so block b is always resident before block b+1 spins (no deadlock
-//     whatever the residency).
+//   * 32/P rows per warp; warps hand the last row's results to the next warp through LL-style lines
+//     {fx, flag, fy, flag} (16-byte single-instruction stores, each 8-byte half self-validating, no fences, so L1 is
+//     never invalidated): 64-entry shared-memory rings inside a CTA (flag = lap number, back-pressure through a
+//     progress counter), full-width arrays in global memory between CTAs, read by a dedicated "poller" warp that
+//     forwards them into ring 0 so that no compute warp ever waits on an L2 round trip.
+//   * persistent CTAs: the grid is only as wide as the wavefront (front + margin); a CTA takes the next row-block
+//     ticket when it finishes one.  Tickets are handed out in row-block order, so the block a CTA waits on is always
+//     being processed or done (no deadlock whatever the residency).  Warps queued behind the front sleep-poll.
+//   * measured (profiles/): the step is bound by the in-order dependent instruction chain of one warp (~1400 cycles
+//     for ~270-450 instructions), not by memory; throughput comes from interleaving independent wavefronts (both
+//     directions, several pairs) on the same schedulers -- < 30 KB of shared memory and < 100 registers per thread
+//     keep several sweep CTAs resident per SM.
 #include <cstdlib>
 #include <type_traits>
 
@@ -227,9 +230,7 @@ __device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float y
         // cp.async.ca into a scratch slot allocates the line in L1 and never blocks (its data is not used)
         int pi = gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
         pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
-#ifndef PF_EXP_NOTOUCH
         cp_async16(k.touch, k.G1s + pi);
-#endif
     }
     float g1x, g1y;
     {
@@ -260,6 +261,94 @@ __device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float y
     err = fadd(err, ry);
     err = fadd(err, rx);
     return err;
+}
+
+// The three probes f, f+(eps,0), f+(0,eps) of ONE candidate on one lane (2 or 1 lanes per row).  The probes almost always
+// fall into the same bilinear cell: the four texels are gathered once and re-gathered (warp-uniform branch) only when
+// some lane's probe crosses a cell boundary.
+struct SkewCell { int gi; float xR, yR; };
+
+template <int POSX>
+__device__ __forceinline__ SkewCell skew_cell(const SweepConst& k, float mxr, float myr) {
+    const float mx = fminf(fmaxf(mxr, 0.0f), k.wm2), my = fminf(fmaxf(myr, 0.0f), k.hm2);
+    const int x0 = __float2int_rz(mx), y0 = __float2int_rz(my);
+    SkewCell c;
+    c.xR = fsub(mx, truncf(mx)); c.yR = fsub(my, truncf(my));
+    c.gi = (x0 + y0) * k.pitch + (POSX ? x0 : y0);
+    return c;
+}
+
+struct SkewTaps { float2 f00, f10, f01, f11; };
+
+template <int POSX>
+__device__ __forceinline__ SkewTaps skew_gather(const SweepConst& k, int gi) {
+    const float2* p00 = k.G1s + gi;
+    const float2* p1 = p00 + k.pitch;            // anti-diagonal +1: (x0,y0+1) and (x0+1,y0) are adjacent
+    const float2* p2 = p1 + k.pitch;             // anti-diagonal +2
+    SkewTaps t;
+    t.f00 = __ldg(p00);
+    t.f10 = __ldg(p1 + (POSX ? 1 : 0));
+    t.f01 = __ldg(p1 + (POSX ? 0 : 1));
+    t.f11 = __ldg(p2 + 1);
+    return t;
+}
+
+template <bool SLOW>
+__device__ __forceinline__ float err_from_taps(const SweepConst& k, const SkewTaps& t, float xR, float yR, float2 g0, float2 bl,
+                                               float fx, float fy, unsigned& tiny) {
+    float g1x, g1y;
+    {
+        const float a2 = fsub(t.f10.x, t.f00.x), a3 = fsub(t.f01.x, t.f00.x);
+        const float a4 = fsub(fsub(fadd(t.f00.x, t.f11.x), t.f10.x), t.f01.x);
+        g1x = fadd(fadd(fadd(t.f00.x, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
+    }
+    {
+        const float a2 = fsub(t.f10.y, t.f00.y), a3 = fsub(t.f01.y, t.f00.y);
+        const float a4 = fsub(fsub(fadd(t.f00.y, t.f11.y), t.f10.y), t.f01.y);
+        g1y = fadd(fadd(fadd(t.f00.y, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
+    }
+    const float dX = fsub(bl.x, fx), dY = fsub(bl.y, fy);
+    const float ss = fadd(fmul(dX, dX), fmul(dY, dY));
+    const float ex = fsub(g0.x, g1x), ey = fsub(g0.y, g1y);
+    const float gs = fadd(fmul(ex, ex), fmul(ey, ey));
+    const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
+    float smooth, grad, ry, rx;
+    if (SLOW) {
+        smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
+        ry = __fdiv_rn(ty, k.fw); rx = __fdiv_rn(tx, k.fw);
+    } else {
+        smooth = sqrt_exact_fast(ss); grad = sqrt_exact_fast(gs);
+        ry = div_by_const(ty, k.fw, k.rcp_w); rx = div_by_const(tx, k.fw, k.rcp_w);
+        tiny = min(tiny, min(min(tiny_key(ss), tiny_key(gs)), min(tiny_key(ty), tiny_key(tx))));
+    }
+    float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
+    err = fadd(err, ry);
+    err = fadd(err, rx);
+    return err;
+}
+
+template <int POSX, bool SLOW>
+__device__ __forceinline__ void eval_err3(const SweepConst& k, float xf, float yf, float2 g0, float2 bl, float2 cand,
+                                          float v[3], unsigned& tiny) {
+    const float fx0 = fadd(cand.x, 0.0f), fy0 = fadd(cand.y, 0.0f);
+    const float fx1 = fadd(cand.x, PF_GRAD_EPS), fy2 = fadd(cand.y, PF_GRAD_EPS);
+    const SkewCell c0 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy0));
+    const SkewCell c1 = skew_cell<POSX>(k, fadd(xf, fx1), fadd(yf, fy0));
+    const SkewCell c2 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy2));
+    const SkewTaps t0 = skew_gather<POSX>(k, c0.gi);
+    {   // warm L1 with the anti-diagonal the gather reaches a few steps from now (asynchronous copy into a scratch slot)
+        int pi = c0.gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
+        pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
+        cp_async16(k.touch, k.G1s + pi);
+    }
+    SkewTaps t1 = t0, t2 = t0;
+    if (__any_sync(0xffffffffu, c1.gi != c0.gi || c2.gi != c0.gi)) {     // rare: a probe crossed a texel boundary
+        t1 = skew_gather<POSX>(k, c1.gi);
+        t2 = skew_gather<POSX>(k, c2.gi);
+    }
+    v[0] = err_from_taps<SLOW>(k, t0, c0.xR, c0.yR, g0, bl, fx0, fy0, tiny);
+    v[1] = err_from_taps<SLOW>(k, t1, c1.xR, c1.yR, g0, bl, fx1, fy0, tiny);
+    v[2] = err_from_taps<SLOW>(k, t2, c2.xR, c2.yR, g0, bl, fx0, fy2, tiny);
 }
 
 // From the six errors {L, L+dx, L+dy, U, U+dx, U+dy} of a pixel to its result: finish both candidates' gradient steps
@@ -434,19 +523,19 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
             float vmax = 0.0f;
             auto run = [&](auto slow_tag) {
                 constexpr bool SLOW = decltype(slow_tag)::value;
+                if constexpr (P == 8) {
+                    const float2 cand = candUp8 ? up : res;
+                    unsigned t1 = 0xffffffffu;
+                    v[0] = eval_err<POSX, SLOW>(k, xf, yf, g0, bl, fadd(cand.x, offx8), fadd(cand.y, offy8), t1);
+                    tkey = min(tkey, t1);
+                } else if constexpr (P == 2) {
+                    eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, sub != 0 ? up : res, v, tkey);
+                } else {
+                    eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, res, v, tkey);
+                    eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, up, v + 3, tkey);
+                }
 #pragma unroll
                 for (int q = 0; q < G::NQ; ++q) {
-                    bool cu; float ox, oy;
-                    if (P == 8) { cu = candUp8; ox = offx8; oy = offy8; }
-                    else {
-                        const int probe = q % 3;
-                        cu = P == 2 ? (sub != 0) : (q >= 3);
-                        ox = probe == 1 ? PF_GRAD_EPS : 0.0f; oy = probe == 2 ? PF_GRAD_EPS : 0.0f;
-                    }
-                    const float2 cand = cu ? up : res;
-                    unsigned t1 = 0xffffffffu;
-                    v[q] = eval_err<POSX, SLOW>(k, xf, yf, g0, bl, fadd(cand.x, ox), fadd(cand.y, oy), t1);
-                    tkey = min(tkey, t1);
                     vmax = fmaxf(vmax, fabsf(v[q]));
                     if (!(v[q] == v[q])) vmax = __int_as_float(0x7f800000);      // NaN -> flagged
                 }
@@ -479,11 +568,7 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
         res.y = valid ? out.y : res.y;
         // ---- results: flow (row-major, only where alpha > 0.9) and the hand-off of the warp's last row ----
         const int x = DIR > 0 ? i : w - 1 - i;
-#ifndef PF_EXP_NOSTORE
         if (active && sub == 0) flow_row[x] = out;
-#else
-        if (active && sub == 0 && out.x == 12345.678f) flow_row[x] = out;
-#endif
         const int i_last = s - (G::ROWS - 1);                 // column of the warp's last row (warp-uniform)
         if (ring_out && i_last >= out_limit)                  // back-pressure, rare: wait until the slot is free
             while (i_last >= out_limit) out_limit = ld_volatile_shared_s32(prog_out) + SW_LL_RING;
