@@ -31,6 +31,13 @@ constexpr int MH = MTH + 2 * MR;         // 12
 
 enum { MODE_PLAIN = 0, MODE_PREP = 1, MODE_DIFFUSE = 2 };
 
+// BORDER_REFLECT_101 with a single reflection, then clamped (exact for -n < p < 2n-1, any valid index otherwise)
+__device__ __forceinline__ int reflect1_clamped(int p, int n) {
+    p = p < 0 ? -p : p;
+    p = p >= n ? 2 * n - 2 - p : p;
+    return clampi(p, 0, n - 1);
+}
+
 // 15x15 sigma 8 Gaussian of the 2-channel flow: row pass left-to-right over the 15 taps, column pass in the symmetric
 // form, both from shared memory.
 template <int MODE>
@@ -41,11 +48,19 @@ k_blur15(const float2* __restrict__ flow, float2* __restrict__ out, int h, int w
     __shared__ float2 s_row[BH][TILE];       // row pass
     const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * BTH;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * TILE + tx;
-    for (int e = tid; e < BH * BW; e += TILE * BTH) {
-        const int ly = e / BW, lx = e - ly * BW;
-        const int gy = reflect101(y0 - BR + ly, h), gx = reflect101(x0 - BR + lx, w);
-        s_in[ly][lx] = flow[(size_t)gy * w + gx];
+    {   // tile + halo: each thread fetches (up to) 2 columns x 2 rows; reflect-101 indices computed once per thread.
+        // One reflection suffices for every position a valid output needs (w, h > 7); positions only reached by
+        // out-of-image threads are clamped.
+        const int gx0 = reflect1_clamped(x0 - BR + tx, w), gx1 = reflect1_clamped(x0 - BR + tx + TILE, w);
+        const int gy0 = reflect1_clamped(y0 - BR + ty, h), gy1 = reflect1_clamped(y0 - BR + ty + BTH, h);
+        const float2* r0 = flow + gy0 * w;
+        const float2* r1 = flow + gy1 * w;
+        s_in[ty][tx] = r0[gx0];
+        if (tx < BW - TILE) s_in[ty][tx + TILE] = r0[gx1];
+        if (ty < BH - BTH) {
+            s_in[ty + BTH][tx] = r1[gx0];
+            if (tx < BW - TILE) s_in[ty + BTH][tx + TILE] = r1[gx1];
+        }
     }
     __syncthreads();
     for (int ly = ty; ly < BH; ly += BTH) {
@@ -91,11 +106,17 @@ k_median5(const float2* __restrict__ src, float2* __restrict__ dst, const float2
     __shared__ float2 s_in[MH][MW + 1];
     const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * MTH;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * TILE + tx;
-    for (int e = tid; e < MH * MW; e += TILE * MTH) {
-        const int ly = e / MW, lx = e - ly * MW;
-        const int gy = clampi(y0 - MR + ly, 0, h - 1), gx = clampi(x0 - MR + lx, 0, w - 1);
-        s_in[ly][lx] = src[(size_t)gy * w + gx];
+    {   // tile + halo: (up to) 2 columns x 2 rows per thread, replicate indices computed once per thread
+        const int gx0 = clampi(x0 - MR + tx, 0, w - 1), gx1 = clampi(x0 - MR + tx + TILE, 0, w - 1);
+        const int gy0 = clampi(y0 - MR + ty, 0, h - 1), gy1 = clampi(y0 - MR + ty + MTH, 0, h - 1);
+        const float2* r0 = src + gy0 * w;
+        const float2* r1 = src + gy1 * w;
+        s_in[ty][tx] = r0[gx0];
+        if (tx < MW - TILE) s_in[ty][tx + TILE] = r0[gx1];
+        if (ty < MH - MTH) {
+            s_in[ty + MTH][tx] = r1[gx0];
+            if (tx < MW - TILE) s_in[ty + MTH][tx + TILE] = r1[gx1];
+        }
     }
     __syncthreads();
     const int x = x0 + tx, y = y0 + ty;

@@ -124,18 +124,36 @@ __device__ __forceinline__ void linear_coord_x(int d, double scale, int sw, int&
     if (s >= sw - 1) { s = sw - 1; f = 0.0f; }
 }
 
+// Resize coordinates are computed in double precision exactly like OpenCV does -- once per CTA column / row into
+// shared memory instead of once per pixel (the FP64 sequence was the bulk of this kernel's instructions).
 __global__ void __launch_bounds__(256)
 k_pyr_down(PlaneSet ps, int sh, int sw, int dh, int dw, double scale_x, double scale_y) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    __shared__ int s_xs[32];
+    __shared__ float s_xf[32];
+    __shared__ int s_y0[8], s_y1[8];
+    __shared__ float s_fy[8];
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (threadIdx.y == 0) {
+        int s_; float f_;
+        linear_coord_x(x < dw ? x : dw - 1, scale_x, sw, s_, f_);
+        s_xs[threadIdx.x] = s_; s_xf[threadIdx.x] = f_;
+    } else if (threadIdx.y == 1 && threadIdx.x < 8) {
+        const int yy = blockIdx.y * 8 + threadIdx.x;
+        int sy; float fy;
+        resize_coord(yy < dh ? yy : dh - 1, scale_y, sy, fy);
+        s_y0[threadIdx.x] = clampi(sy, 0, sh - 1);
+        s_y1[threadIdx.x] = clampi(sy + 1, 0, sh - 1);
+        s_fy[threadIdx.x] = fy;
+    }
+    __syncthreads();
     if (x >= dw || y >= dh) return;
     const float* __restrict__ src = ps.src[blockIdx.z];
     float* __restrict__ dst = ps.dst[blockIdx.z];
-    int s, sy; float f, fy;
-    linear_coord_x(x, scale_x, sw, s, f);
-    resize_coord(y, scale_y, sy, fy);
-    const float* S0 = src + (size_t)clampi(sy, 0, sh - 1) * sw;
-    const float* S1 = src + (size_t)clampi(sy + 1, 0, sh - 1) * sw;
+    const int s = s_xs[threadIdx.x];
+    const float f = s_xf[threadIdx.x], fy = s_fy[threadIdx.y];
+    const float* S0 = src + s_y0[threadIdx.y] * sw;
+    const float* S1 = src + s_y1[threadIdx.y] * sw;
     float r0, r1;
     if (s >= sw - 1) { r0 = S0[s]; r1 = S1[s]; }
     else {
@@ -143,7 +161,7 @@ k_pyr_down(PlaneSet ps, int sh, int sw, int dh, int dw, double scale_x, double s
         r0 = fadd(fmul(S0[s], g), fmul(S0[s + 1], f));
         r1 = fadd(fmul(S1[s], g), fmul(S1[s + 1], f));
     }
-    dst[(size_t)y * dw + x] = fadd(fmul(r0, fsub(1.0f, fy)), fmul(r1, fy));
+    dst[y * dw + x] = fadd(fmul(r0, fsub(1.0f, fy)), fmul(r1, fy));
 }
 
 void launch_pyr_down(const PlaneSet& ps, int nplanes, int sh, int sw, int dh, int dw, cudaStream_t st) {
@@ -158,26 +176,43 @@ void launch_pyr_down(const PlaneSet& ps, int nplanes, int sh, int sw, int dh, in
 // ====================================================================================================
 // gradients: Sobel k=1 (replicate) then 3x3 sigma 0.5 blur (reflect-101), output interleaved (Ix, Iy)
 // ====================================================================================================
+// Tile of 32 x 8 outputs from a shared-memory tile of I with a 2-pixel halo.  Sobel uses replicated borders, the 3x3
+// blur reflect-101 of the Sobel image; both index maps stay within 2 pixels of the output position, so every tap is a
+// shared-memory read at (global index - tile origin).
 __global__ void __launch_bounds__(256)
 k_gradient(const float* __restrict__ I, float2* __restrict__ G, int h, int w) {
     PF_GAUSS_TABLES
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    __shared__ float s_I[12][36 + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    {
+        const int gx0 = clampi(x0 - 2 + tx, 0, w - 1), gx1 = clampi(x0 - 2 + tx + 32, 0, w - 1);
+        const int gy0 = clampi(y0 - 2 + ty, 0, h - 1), gy1 = clampi(y0 - 2 + ty + 8, 0, h - 1);
+        s_I[ty][tx] = I[gy0 * w + gx0];
+        if (tx < 4) s_I[ty][tx + 32] = I[gy0 * w + gx1];
+        if (ty < 4) {
+            s_I[ty + 8][tx] = I[gy1 * w + gx0];
+            if (tx < 4) s_I[ty + 8][tx + 32] = I[gy1 * w + gx1];
+        }
+    }
+    __syncthreads();
+    const int x = x0 + tx, y = y0 + ty;
     if (x >= w || y >= h) return;
-    int xs[3] = { reflect101(x - 1, w), x, reflect101(x + 1, w) };
+    // local (shared-memory) coordinates of global column c / row r: c - (x0 - 2), r - (y0 - 2).  Positions outside the
+    // image were loaded with replicated values, which is exactly what the clamped Sobel taps read.
+    const int ox = x0 - 2, oy = y0 - 2;
+    const int xs[3] = { reflect101(x - 1, w), x, reflect101(x + 1, w) };
     float rx[3], ry[3];
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
         const int yy = reflect101(y + dy, h);
-        const float* R = I + (size_t)yy * w;
-        const float* Rp = I + (size_t)clampi(yy + 1, 0, h - 1) * w;
-        const float* Rm = I + (size_t)clampi(yy - 1, 0, h - 1) * w;
+        const int ly = yy - oy, lyp = clampi(yy + 1, 0, h - 1) - oy, lym = clampi(yy - 1, 0, h - 1) - oy;
         float sx[3], sy[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int xx = xs[k];
-            sx[k] = fsub(R[clampi(xx + 1, 0, w - 1)], R[clampi(xx - 1, 0, w - 1)]);
-            sy[k] = fsub(Rp[xx], Rm[xx]);
+            sx[k] = fsub(s_I[ly][clampi(xx + 1, 0, w - 1) - ox], s_I[ly][clampi(xx - 1, 0, w - 1) - ox]);
+            sy[k] = fsub(s_I[lyp][xx - ox], s_I[lym][xx - ox]);
         }
         rx[dy + 1] = fadd(fmul(sx[1], kG3H[0]), fmul(fadd(sx[0], sx[2]), kG3H[1]));
         ry[dy + 1] = fadd(fmul(sy[1], kG3H[0]), fmul(fadd(sy[0], sy[2]), kG3H[1]));
@@ -185,7 +220,7 @@ k_gradient(const float* __restrict__ I, float2* __restrict__ G, int h, int w) {
     float2 o;
     o.x = fadd(fmul(kG3H[0], rx[1]), fmul(kG3H[1], fadd(rx[2], rx[0])));
     o.y = fadd(fmul(kG3H[0], ry[1]), fmul(kG3H[1], fadd(ry[2], ry[0])));
-    G[(size_t)y * w + x] = o;
+    G[y * w + x] = o;
     (void)kG5; (void)kG3O; (void)kG15;
 }
 
@@ -200,19 +235,37 @@ void launch_gradient(const float* I, float2* G, int h, int w, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, float2* __restrict__ dst, int dh, int dw,
                  double scale_x, double scale_y) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    __shared__ int s_sx[32], s_sy[8];
+    __shared__ float s_ca[32][4], s_cb[8][4];
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (threadIdx.y == 0) {
+        int s_; float f, c[4];
+        resize_coord(x < dw ? x : dw - 1, scale_x, s_, f); cubic_coeffs(f, c);
+        s_sx[threadIdx.x] = s_;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_ca[threadIdx.x][k] = c[k];
+    } else if (threadIdx.y == 1 && threadIdx.x < 8) {
+        const int yy = blockIdx.y * 8 + threadIdx.x;
+        int s_; float f, c[4];
+        resize_coord(yy < dh ? yy : dh - 1, scale_y, s_, f); cubic_coeffs(f, c);
+        s_sy[threadIdx.x] = s_;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_cb[threadIdx.x][k] = c[k];
+    }
+    __syncthreads();
     if (x >= dw || y >= dh) return;
-    int sx, sy; float f, ca[4], cb[4];
-    resize_coord(x, scale_x, sx, f); cubic_coeffs(f, ca);
-    resize_coord(y, scale_y, sy, f); cubic_coeffs(f, cb);
+    const int sx = s_sx[threadIdx.x], sy = s_sy[threadIdx.y];
+    float ca[4], cb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ca[k] = s_ca[threadIdx.x][k]; cb[k] = s_cb[threadIdx.y][k]; }
     int xs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) xs[k] = clampi(sx - 1 + k, 0, sw - 1);
     float rx[4], ry[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float2* S = src + (size_t)clampi(sy - 1 + k, 0, sh - 1) * sw;
+        const float2* S = src + clampi(sy - 1 + k, 0, sh - 1) * sw;
         const float2 v0 = S[xs[0]], v1 = S[xs[1]], v2 = S[xs[2]], v3 = S[xs[3]];
         rx[k] = fadd(fadd(fadd(fmul(v0.x, ca[0]), fmul(v1.x, ca[1])), fmul(v2.x, ca[2])), fmul(v3.x, ca[3]));
         ry[k] = fadd(fadd(fadd(fmul(v0.y, ca[0]), fmul(v1.y, ca[1])), fmul(v2.y, ca[2])), fmul(v3.y, ca[3]));
@@ -227,7 +280,7 @@ k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, float2* __restr
         ox = fadd(fadd(fadd(fmul(rx[0], cb[0]), fmul(rx[1], cb[1])), fmul(rx[2], cb[2])), fmul(rx[3], cb[3]));
         oy = fadd(fadd(fadd(fmul(ry[0], cb[0]), fmul(ry[1], cb[1])), fmul(ry[2], cb[2])), fmul(ry[3], cb[3]));
     }
-    dst[(size_t)y * dw + x] = make_float2(fmul(ox, PF_INV_PYR), fmul(oy, PF_INV_PYR));
+    dst[y * dw + x] = make_float2(fmul(ox, PF_INV_PYR), fmul(oy, PF_INV_PYR));
 }
 
 void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int dh, int dw, cudaStream_t st) {
@@ -240,56 +293,67 @@ void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int d
 // ====================================================================================================
 // tail: INTER_LINEAR to (rows x pcols), *2, 3x3 sigma 1 blur; writes the cropped columns only
 // ====================================================================================================
-struct LinTap { int s; float f; bool edge; };
-
+// Tile of 32 x 8 outputs: the INTER_LINEAR-upsampled (x2-scaled) flow is computed ONCE per position of the tile + 1 px
+// halo into shared memory (reflect-101 of the 3x3 blur applied to the coordinates of the padded full-size image), then
+// the 3x3 sigma-1 row and column passes run from shared memory.
 __global__ void __launch_bounds__(256)
 k_tail(const float2* __restrict__ src, int sh, int sw, int rows, int pcols, int pad, int cols,
        float2* __restrict__ out, size_t out_stride, double scale_x, double scale_y) {
     PF_GAUSS_TABLES
-    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (xo >= cols || y >= rows) return;
-    const int x = xo + pad;
-    LinTap tx[3];
-    int y0[3], y1[3]; float fy[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int xx = reflect101(x + k - 1, pcols);
-        linear_coord_x(xx, scale_x, sw, tx[k].s, tx[k].f);
-        tx[k].edge = tx[k].s >= sw - 1;
-        const int yy = reflect101(y + k - 1, rows);
-        int sy;
-        resize_coord(yy, scale_y, sy, fy[k]);
-        y0[k] = clampi(sy, 0, sh - 1);
-        y1[k] = clampi(sy + 1, 0, sh - 1);
+    __shared__ int s_xs[34];
+    __shared__ float s_xf[34];
+    __shared__ int s_y0[10], s_y1[10];
+    __shared__ float s_fy[10];
+    __shared__ float2 s_up[10][34];
+    __shared__ float2 s_rb[10][32];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int xo0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    if (tid < 34) {                       // columns xo0-1 .. xo0+32 of the crop = padded columns (+pad), reflected
+        const int xx = reflect101(xo0 + pad - 1 + tid, pcols);
+        int s_; float f_;
+        linear_coord_x(xx, scale_x, sw, s_, f_);
+        s_xs[tid] = s_; s_xf[tid] = f_;
+    } else if (tid >= 64 && tid < 74) {   // rows y0-1 .. y0+8, reflected
+        const int k = tid - 64;
+        const int yy = reflect101(y0 - 1 + k, rows);
+        int sy; float fy;
+        resize_coord(yy, scale_y, sy, fy);
+        s_y0[k] = clampi(sy, 0, sh - 1);
+        s_y1[k] = clampi(sy + 1, 0, sh - 1);
+        s_fy[k] = fy;
     }
-    float rbx[3], rby[3];   // row-blurred values for rows y-1, y, y+1
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const float2* S0 = src + (size_t)y0[r] * sw;
-        const float2* S1 = src + (size_t)y1[r] * sw;
-        const float b1 = fy[r], b0 = fsub(1.0f, b1);
-        float ux[3], uy[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float2 r0, r1;
-            const int s = tx[k].s;
-            if (tx[k].edge) { r0 = S0[s]; r1 = S1[s]; }
-            else {
-                const float f = tx[k].f, g = fsub(1.0f, f);
-                const float2 a0 = S0[s], a1 = S0[s + 1], c0 = S1[s], c1 = S1[s + 1];
-                r0.x = fadd(fmul(a0.x, g), fmul(a1.x, f)); r0.y = fadd(fmul(a0.y, g), fmul(a1.y, f));
-                r1.x = fadd(fmul(c0.x, g), fmul(c1.x, f)); r1.y = fadd(fmul(c0.y, g), fmul(c1.y, f));
-            }
-            ux[k] = fmul(fadd(fmul(r0.x, b0), fmul(r1.x, b1)), 2.0f);   // flow *= 1/downscaleFactor
-            uy[k] = fmul(fadd(fmul(r0.y, b0), fmul(r1.y, b1)), 2.0f);
+    __syncthreads();
+    for (int e = tid; e < 10 * 34; e += 256) {
+        const int ly = e / 34, lx = e - ly * 34;
+        const float2* S0 = src + s_y0[ly] * sw;
+        const float2* S1 = src + s_y1[ly] * sw;
+        const int s = s_xs[lx];
+        const float b1 = s_fy[ly], b0 = fsub(1.0f, b1);
+        float2 r0, r1;
+        if (s >= sw - 1) { r0 = S0[s]; r1 = S1[s]; }
+        else {
+            const float f = s_xf[lx], g = fsub(1.0f, f);
+            const float2 a0 = S0[s], a1 = S0[s + 1], c0 = S1[s], c1 = S1[s + 1];
+            r0.x = fadd(fmul(a0.x, g), fmul(a1.x, f)); r0.y = fadd(fmul(a0.y, g), fmul(a1.y, f));
+            r1.x = fadd(fmul(c0.x, g), fmul(c1.x, f)); r1.y = fadd(fmul(c0.y, g), fmul(c1.y, f));
         }
-        rbx[r] = fadd(fmul(ux[1], kG3O[0]), fmul(fadd(ux[0], ux[2]), kG3O[1]));
-        rby[r] = fadd(fmul(uy[1], kG3O[0]), fmul(fadd(uy[0], uy[2]), kG3O[1]));
+        s_up[ly][lx] = make_float2(fmul(fadd(fmul(r0.x, b0), fmul(r1.x, b1)), 2.0f),      // flow *= 1/downscaleFactor
+                                   fmul(fadd(fmul(r0.y, b0), fmul(r1.y, b1)), 2.0f));
     }
+    __syncthreads();
+    for (int e = tid; e < 10 * 32; e += 256) {      // row pass of the 3x3 blur
+        const int ly = e >> 5, lx = e & 31;
+        const float2 l = s_up[ly][lx], c = s_up[ly][lx + 1], r = s_up[ly][lx + 2];
+        s_rb[ly][lx] = make_float2(fadd(fmul(c.x, kG3O[0]), fmul(fadd(l.x, r.x), kG3O[1])),
+                                   fadd(fmul(c.y, kG3O[0]), fmul(fadd(l.y, r.y), kG3O[1])));
+    }
+    __syncthreads();
+    const int xo = xo0 + tx, y = y0 + ty;
+    if (xo >= cols || y >= rows) return;
+    const float2 u = s_rb[ty][tx], c = s_rb[ty + 1][tx], d = s_rb[ty + 2][tx];
     float2 o;
-    o.x = fadd(fmul(kG3O[0], rbx[1]), fmul(kG3O[1], fadd(rbx[2], rbx[0])));
-    o.y = fadd(fmul(kG3O[0], rby[1]), fmul(kG3O[1], fadd(rby[2], rby[0])));
+    o.x = fadd(fmul(kG3O[0], c.x), fmul(kG3O[1], fadd(d.x, u.x)));
+    o.y = fadd(fmul(kG3O[0], c.y), fmul(kG3O[1], fadd(d.y, u.y)));
     *reinterpret_cast<float2*>(reinterpret_cast<char*>(out) + (size_t)y * out_stride + (size_t)xo * sizeof(float2)) = o;
     (void)kG5; (void)kG3H; (void)kG15;
 }
