@@ -93,6 +93,23 @@ PF_API int pf_novel_view(pf_engine* engine,
                          void* flow_l_to_r, size_t stride_lr,
                          void* flow_r_to_l, size_t stride_rl);
 
+/* First "next" row of the path: Stitchtools::prepare(colorImageL, colorImageR), CPU/StitchTool.cpp:7-36,
+ * up to but EXCLUDING the blend smoothing of GenerateBlend (:133-145, order-dependent OpenCV ROI box filtering, left to the
+ * host as in the reference's own GPU build).  Produces getMap() (CV_8UC1: 100 = L only, 50 = R only, 150 = overlap),
+ * getOverlappedL()/getOverlappedR() (CV_8UC4, the inputs of pf_prepare_bidirectional), the un-smoothed blend (CV_32FC1) of
+ * GenerateBlend :113-124 + countblend :148-191 (replaces countblend_Kernel, GPU/StitchTool_GPU.cu:10-66) and MergedDis.
+ * Any output pointer may be NULL.  Images smaller than 200 px in their shorter side are rejected (the reference's search
+ * step cols/200 would be 0 and its loop would not terminate).  HOST or DEVICE pointers, strides in bytes. */
+PF_API int pf_stitch_prepare(pf_engine* engine,
+                             const void* image_l, size_t stride_l,
+                             const void* image_r, size_t stride_r,
+                             int rows, int cols,
+                             void* map_u8, size_t stride_map,
+                             void* overlapped_l, size_t stride_ol,
+                             void* overlapped_r, size_t stride_or,
+                             void* blend_raw, size_t stride_blend,
+                             void* merged_dis, size_t stride_dis);
+
 /* Pinned host memory for zero-staging transfers (optional; any host pointer is accepted by the calls above). */
 PF_API int pf_host_alloc(void** ptr, size_t bytes);
 PF_API int pf_host_free(void* ptr);

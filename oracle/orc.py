@@ -237,3 +237,28 @@ def combine_novel_views(imageL, imageR, flowLtoR, flowRtoL, blend):
     lib().orc_combine_novel_views(pl, C.c_size_t(cols * 4), pr, C.c_size_t(cols * 4), plr, prl, pb, rows, cols,
                                   out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def stitch_match_and_mask(imageL, imageR):
+    """Stitchtools::MatchImages + the overlap masking of Stitchtools::prepare (CPU/StitchTool.cpp:7-50)."""
+    L, pl = _u(imageL)
+    R, pr = _u(imageR)
+    rows, cols, _ = L.shape
+    m = np.empty((rows, cols), np.uint8)
+    oL = np.empty((rows, cols, 4), np.uint8)
+    oR = np.empty((rows, cols, 4), np.uint8)
+    lib().orc_stitch_match_and_mask(pl, C.c_size_t(cols * 4), pr, C.c_size_t(cols * 4), rows, cols,
+                                    m.ctypes.data_as(C.c_void_p), oL.ctypes.data_as(C.c_void_p), oR.ctypes.data_as(C.c_void_p))
+    return m, oL, oR
+
+
+def stitch_blend_raw(map_u8):
+    """GenerateBlend before the smoothing (CPU/StitchTool.cpp:98-131, countblend :148-191) -> (blend, MergedDis)."""
+    m, pm = _u(map_u8)
+    rows, cols = m.shape
+    blend = np.empty((rows, cols), np.float32)
+    md = np.empty((rows, cols), np.float32)
+    rc = lib().orc_stitch_blend_raw(pm, rows, cols, blend.ctypes.data_as(C.c_void_p), md.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError("image too small: the reference's search step cols/200 (rows/200) is 0")
+    return blend, md

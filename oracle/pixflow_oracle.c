@@ -748,3 +748,87 @@ ORC_API int orc_combine_novel_views(const uint8_t* imageL, size_t strideL, const
         }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Section C: first "next" row: Stitchtools::prepare without the blend     */
+/* smoothing -- CPU/StitchTool.cpp:7-50 (MatchImages, overlap masking) and :98-131, :148-191      */
+/* (GenerateBlend up to the block-wise blur, countblend).                                         */
+/* ------------------------------------------------------------------------------------------ */
+
+/* MatchImages (:38-50): Map = (alphaL > 0 ? 100 : 0) + (alphaR > 0 ? 50 : 0); prepare (:16-33): both images are
+ * multiplied by (Map > 140), i.e. kept only inside the overlap. */
+ORC_API void orc_stitch_match_and_mask(const uint8_t* L, size_t strideL, const uint8_t* R, size_t strideR, int rows, int cols,
+                                       uint8_t* map, uint8_t* overlappedL, uint8_t* overlappedR) {
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const uint8_t* l = L + (size_t)y * strideL + (size_t)x * 4;
+            const uint8_t* r = R + (size_t)y * strideR + (size_t)x * 4;
+            const int m = (l[3] > 0 ? 100 : 0) + (r[3] > 0 ? 50 : 0);
+            map[(size_t)y * cols + x] = (uint8_t)m;
+            const int keep = m > 140 ? 1 : 0;
+            for (int c = 0; c < 4; ++c) {
+                overlappedL[((size_t)y * cols + x) * 4 + c] = (uint8_t)(l[c] * keep);
+                overlappedR[((size_t)y * cols + x) * 4 + c] = (uint8_t)(r[c] * keep);
+            }
+        }
+}
+
+/* countblend (:148-191) on the circularly extended map (extension by len = cols/5 on both sides, :101-111);
+ * x is an extended column.  Returns blend and writes the smaller distance to *merged_dis. */
+static float stitch_countblend(const uint8_t* emap, int rows, int cols, int ecols, int x, int y, float* merged_dis) {
+    const int step = (cols <= rows) ? cols / 200 : rows / 200;
+    float minLdis = (float)(10 * cols), minRdis = (float)(10 * cols);
+#define EM(yy, xx) emap[(size_t)(yy) * ecols + (xx)]
+    for (int i = 0; i < cols / 2; i = i + step) {
+        if (x + i < ecols && EM(y, x + i) == 100 && i < minLdis) minLdis = i;
+        if (x + i < ecols && EM(y, x + i) == 50 && i < minRdis) minRdis = i;
+        if (x - i > 0 && EM(y, x - i) == 100 && i < minLdis) minLdis = i;
+        if (x - i > 0 && EM(y, x - i) == 50 && i < minRdis) minRdis = i;
+        if (y + i < rows && EM(y + i, x) == 100 && i < minLdis) minLdis = i;
+        if (y + i < rows && EM(y + i, x) == 50 && i < minRdis) minRdis = i;
+        if (y - i > 0 && EM(y - i, x) == 100 && i < minLdis) minLdis = i;
+        if (y - i > 0 && EM(y - i, x) == 50 && i < minRdis) minRdis = i;
+        if ((x + i < ecols && y + i < rows) && EM(y + i, x + i) == 100 && i * sqrt(2) < minLdis) minLdis = i * sqrt(2);
+        if ((x + i < ecols && y + i < rows) && EM(y + i, x + i) == 50 && i * sqrt(2) < minRdis) minRdis = i * sqrt(2);
+        if ((x - i > 0 && y - i > 0) && EM(y - i, x - i) == 100 && i * sqrt(2) < minLdis) minLdis = i * sqrt(2);
+        if ((x - i > 0 && y - i > 0) && EM(y - i, x - i) == 50 && i * sqrt(2) < minRdis) minRdis = i * sqrt(2);
+        if ((x + i < ecols && y - i > 0) && EM(y - i, x + i) == 100 && i * sqrt(2) < minLdis) minLdis = i * sqrt(2);
+        if ((x + i < ecols && y - i > 0) && EM(y - i, x + i) == 50 && i * sqrt(2) < minRdis) minRdis = i * sqrt(2);
+        if ((x - i > 0 && y + i < rows) && EM(y + i, x - i) == 100 && i * sqrt(2) < minLdis) minLdis = i * sqrt(2);
+        if ((x - i > 0 && y + i < rows) && EM(y + i, x - i) == 50 && i * sqrt(2) < minRdis) minRdis = i * sqrt(2);
+    }
+#undef EM
+    const float blend = minLdis / (minRdis + minLdis);
+    *merged_dis = (minLdis < minRdis) ? minLdis : minRdis;
+    return blend;
+}
+
+/* GenerateBlend (:98-131) before the smoothing: blend (rows x cols) and MergedDis cropped back to rows x cols.
+ * Returns 1 if the image is too small for the reference's loop step (cols/200 or rows/200 == 0: the reference would
+ * never terminate), 0 otherwise. */
+ORC_API int orc_stitch_blend_raw(const uint8_t* map, int rows, int cols, float* blend, float* merged_dis) {
+    const int step = (cols <= rows) ? cols / 200 : rows / 200;
+    if (step < 1) return 1;
+    const int len = cols / 5, ecols = cols + 2 * len;
+    uint8_t* emap = (uint8_t*)malloc((size_t)rows * ecols);
+    for (int y = 0; y < rows; ++y) {
+        const uint8_t* s = map + (size_t)y * cols;
+        uint8_t* d = emap + (size_t)y * ecols;
+        memcpy(d, s + (cols - len), (size_t)len);
+        memcpy(d + len, s, (size_t)cols);
+        memcpy(d + len + cols, s, (size_t)len);
+    }
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const uint8_t m = emap[(size_t)y * ecols + x + len];
+            float b, md = 0.0f;
+            if (m == 100) b = 0;
+            else if (m == 50) b = 1;
+            else if (m == 150) b = stitch_countblend(emap, rows, cols, ecols, x + len, y, &md);
+            else b = 0.5f;
+            blend[(size_t)y * cols + x] = b;
+            merged_dis[(size_t)y * cols + x] = md;
+        }
+    free(emap);
+    return 0;
+}

@@ -23,6 +23,7 @@ SIGNATURES = {
                                             C.POINTER(_vp), _sz, C.POINTER(_vp), _sz]),
     "pf_combine_novel_views": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
     "pf_novel_view": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "pf_stitch_prepare": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "pf_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "pf_host_free": (_i, [_vp]),
     "pf_kernel_launch_count": (C.c_uint64, []),

@@ -247,3 +247,48 @@ class NovelViewGeneratorAsymmetricFlow(NovelViewGenerator):
 
     def close(self):
         self._alg.close()
+
+
+class Stitchtools:
+    """Stitchtools (CPU/StitchTool.hpp:21-61) -- the part of prepare() that runs on the B200: canvas map, overlap masking
+    and the un-smoothed blend map (MatchImages, GenerateBlend up to :131, countblend).  The block-wise blur that follows
+    in GenerateBlend (CPU/StitchTool.cpp:133-145) is not implemented here."""
+
+    def __init__(self, flowAlg=None, device=-1):
+        self._own = flowAlg is None
+        self._alg = makeOpticalFlowByName("pixflow_low", device) if flowAlg is None else flowAlg
+        self.ImageL = self.ImageR = None
+        self.Map = self.OverlappedL = self.OverlappedR = self.BlendUnsmoothed = self.MergedDis = None
+
+    def prepare(self, colorImageL, colorImageR):
+        self.ImageL = np.array(colorImageL, copy=True)
+        self.ImageR = np.array(colorImageR, copy=True)
+        kl, pl, sl, rows, cols = _view(self.ImageL, np.uint8, 4, "colorImageL")
+        kr, pr, sr, r1, c1 = _view(self.ImageR, np.uint8, 4, "colorImageR")
+        if (rows, cols) != (r1, c1):
+            raise ValueError("colorImageL and colorImageR must have the same size")
+        self.Map = np.empty((rows, cols), np.uint8)
+        self.OverlappedL = np.empty((rows, cols, 4), np.uint8)
+        self.OverlappedR = np.empty((rows, cols, 4), np.uint8)
+        self.BlendUnsmoothed = np.empty((rows, cols), np.float32)
+        self.MergedDis = np.empty((rows, cols), np.float32)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        _lib.check(self._alg._lib.pf_stitch_prepare(
+            self._alg._h, pl, sl, pr, sr, rows, cols, p(self.Map), cols, p(self.OverlappedL), cols * 4,
+            p(self.OverlappedR), cols * 4, p(self.BlendUnsmoothed), cols * 4, p(self.MergedDis), cols * 4))
+
+    def getMap(self):
+        return self.Map
+
+    def getOverlappedL(self):
+        return self.OverlappedL
+
+    def getOverlappedR(self):
+        return self.OverlappedR
+
+    def getBlendUnsmoothed(self):
+        return self.BlendUnsmoothed
+
+    def close(self):
+        if self._own:
+            self._alg.close()

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpixflow_b200.so")
-SOURCES = ["pf_kernels.cu", "pf_sweep.cu", "pf_fused.cu", "pf_selftest.cu", "pf_engine.cu"]
+SOURCES = ["pf_kernels.cu", "pf_sweep.cu", "pf_fused.cu", "pf_stitch.cu", "pf_selftest.cu", "pf_engine.cu"]
 HEADERS = ["pf_kernels.cuh", "pf_math.cuh", "pf_prep.cuh", os.path.join("..", "..", "include", "pixflow_b200.h")]
 
 NVCC_FLAGS = [

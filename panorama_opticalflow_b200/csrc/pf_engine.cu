@@ -449,6 +449,19 @@ int sync_pair(Workspace& w, int ndir) {
 
 }  // namespace
 
+// ---- small RAII device buffer for the synchronous helper entry points ----
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { std::lock_guard<std::mutex> cg(g_capture_mu); cudaFree(p); }
+    int alloc(size_t n) { std::lock_guard<std::mutex> cg(g_capture_mu); PF_CUDA(cudaMalloc(&p, n ? n : 1)); return PF_OK; }
+    int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; PF_CUDA(cudaMemcpy(p, h, n, cudaMemcpyHostToDevice)); return PF_OK; }
+    int download(void* h, size_t n) { PF_CUDA(cudaDeviceSynchronize()); PF_CUDA(cudaGetLastError()); PF_CUDA(cudaMemcpy(h, p, n, cudaMemcpyDeviceToHost)); return PF_OK; }
+    template <class T> T* as() { return (T*)p; }
+};
+#define RC(x) do { int rc_ = (x); if (rc_ != PF_OK) return rc_; } while (0)
+}  // namespace
+
 // ======================================================================================================
 // C-ABI
 // ======================================================================================================
@@ -700,6 +713,49 @@ int pf_novel_view(pf_engine* e, const void* L, size_t sl, const void* R, size_t 
     return collect_sweep_timing(e, used);
 }
 
+int pf_stitch_prepare(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, int rows, int cols,
+                      void* map, size_t sm, void* oL, size_t sol, void* oR, size_t sor, void* blend, size_t sb, void* mdis, size_t sd) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    int rc;
+    if ((rc = check_image_args(L, sl, rows, cols, 4, "colorImageL")) != PF_OK) return rc;
+    if ((rc = check_image_args(R, sr, rows, cols, 4, "colorImageR")) != PF_OK) return rc;
+    if (((cols <= rows) ? cols / 200 : rows / 200) < 1)
+        return fail(PF_ERR_INVALID_ARGUMENT, "image too small for Stitchtools::countblend (shorter side < 200)");
+    if (map && sm < (size_t)cols) return fail(PF_ERR_INVALID_ARGUMENT, "map stride < cols");
+    if (oL && (rc = check_image_args(oL, sol, rows, cols, 4, "OverlappedL")) != PF_OK) return rc;
+    if (oR && (rc = check_image_args(oR, sor, rows, cols, 4, "OverlappedR")) != PF_OK) return rc;
+    if (blend && (rc = check_image_args(blend, sb, rows, cols, 4, "blend")) != PF_OK) return rc;
+    if (mdis && (rc = check_image_args(mdis, sd, rows, cols, 4, "MergedDis")) != PF_OK) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    // device staging (dense) for whatever lives on the host
+    DevBuf dL, dR, dM, dOL, dOR, dB, dD;
+    const size_t n = (size_t)rows * cols;
+    const uint8_t* pL; const uint8_t* pR; size_t psl, psr;
+    if (is_device_ptr(L)) { pL = (const uint8_t*)L; psl = sl; }
+    else { RC(dL.alloc(n * 4)); PF_CUDA(cudaMemcpy2D(dL.p, (size_t)cols * 4, L, sl, (size_t)cols * 4, rows, cudaMemcpyHostToDevice)); pL = dL.as<uint8_t>(); psl = (size_t)cols * 4; }
+    if (is_device_ptr(R)) { pR = (const uint8_t*)R; psr = sr; }
+    else { RC(dR.alloc(n * 4)); PF_CUDA(cudaMemcpy2D(dR.p, (size_t)cols * 4, R, sr, (size_t)cols * 4, rows, cudaMemcpyHostToDevice)); pR = dR.as<uint8_t>(); psr = (size_t)cols * 4; }
+    struct Out { void* user; size_t ustride; DevBuf* buf; size_t elem; uint8_t* dev; size_t dstride; };
+    Out outs[5] = {{map, sm, &dM, 1, nullptr, 0}, {oL, sol, &dOL, 4, nullptr, 0}, {oR, sor, &dOR, 4, nullptr, 0},
+                   {blend, sb, &dB, 4, nullptr, 0}, {mdis, sd, &dD, 4, nullptr, 0}};
+    for (auto& o : outs) {
+        if (o.user && is_device_ptr(o.user)) { o.dev = (uint8_t*)o.user; o.dstride = o.ustride; }
+        else { RC(o.buf->alloc(n * o.elem)); o.dev = o.buf->as<uint8_t>(); o.dstride = (size_t)cols * o.elem; }
+    }
+    pf::launch_stitch_match_mask(pL, psl, pR, psr, rows, cols, outs[0].dev, outs[0].dstride, outs[1].dev, outs[1].dstride,
+                                 outs[2].dev, outs[2].dstride, 0);
+    pf::launch_stitch_blend_raw(outs[0].dev, outs[0].dstride, rows, cols, (float*)outs[3].dev, outs[3].dstride,
+                                (float*)outs[4].dev, outs[4].dstride, 0);
+    LAUNCHED(2);
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaDeviceSynchronize());
+    for (auto& o : outs)
+        if (o.user && !is_device_ptr(o.user))
+            PF_CUDA(cudaMemcpy2D(o.user, o.ustride, o.dev, o.dstride, (size_t)cols * o.elem, rows, cudaMemcpyDeviceToHost));
+    return PF_OK;
+}
+
 int pf_selftest_exact_math(int wmin, int wmax, uint64_t* out4) {
     if (!out4 || wmin < 1 || wmax < wmin) return fail(PF_ERR_INVALID_ARGUMENT, "bad selftest arguments");
     unsigned long long a = 0, b = 0, c = 0;
@@ -722,17 +778,6 @@ int pf_host_free(void* p) {
 }  // extern "C"
 
 // ---- diagnostic single-stage entry points ---------------------------------------------------------------
-namespace {
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { std::lock_guard<std::mutex> cg(g_capture_mu); cudaFree(p); }
-    int alloc(size_t n) { std::lock_guard<std::mutex> cg(g_capture_mu); PF_CUDA(cudaMalloc(&p, n ? n : 1)); return PF_OK; }
-    int upload(const void* h, size_t n) { int rc = alloc(n); if (rc) return rc; PF_CUDA(cudaMemcpy(p, h, n, cudaMemcpyHostToDevice)); return PF_OK; }
-    int download(void* h, size_t n) { PF_CUDA(cudaDeviceSynchronize()); PF_CUDA(cudaGetLastError()); PF_CUDA(cudaMemcpy(h, p, n, cudaMemcpyDeviceToHost)); return PF_OK; }
-    template <class T> T* as() { return (T*)p; }
-};
-#define RC(x) do { int rc_ = (x); if (rc_ != PF_OK) return rc_; } while (0)
-}  // namespace
 
 extern "C" {
 

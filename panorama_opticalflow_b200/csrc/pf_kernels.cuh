@@ -82,6 +82,12 @@ void launch_combine(const uint8_t* imageL, size_t strideL, const uint8_t* imageR
                     const float* blend, size_t strideB, int rows, int cols,
                     uint8_t* out, size_t strideOut, cudaStream_t st);
 
+// ---- Stitchtools::prepare without the blend smoothing (CPU/StitchTool.cpp:7-50, :98-131, :148-191), pf_stitch.cu ------
+void launch_stitch_match_mask(const uint8_t* L, size_t strideL, const uint8_t* R, size_t strideR, int rows, int cols,
+                              uint8_t* map, size_t strideM, uint8_t* oL, size_t strideOL, uint8_t* oR, size_t strideOR, cudaStream_t st);
+void launch_stitch_blend_raw(const uint8_t* map, size_t strideM, int rows, int cols, float* blend, size_t strideB,
+                             float* mdis, size_t strideD, cudaStream_t st);
+
 // ---- exhaustive self-test of the branch-free exact division / square root (pf_selftest.cu) ---------------
 int selftest_exact_math(int wmin, int wmax, unsigned long long* out_mismatch_sqrt, unsigned long long* out_mismatch_eps,
                         unsigned long long* out_mismatch_w, int* out_first_bad_w);
