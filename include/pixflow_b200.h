@@ -93,13 +93,18 @@ PF_API int pf_novel_view(pf_engine* engine,
                          void* flow_l_to_r, size_t stride_lr,
                          void* flow_r_to_l, size_t stride_rl);
 
-/* First "next" row of the path: Stitchtools::prepare(colorImageL, colorImageR), CPU/StitchTool.cpp:7-36,
- * up to but EXCLUDING the blend smoothing of GenerateBlend (:133-145, order-dependent OpenCV ROI box filtering, left to the
- * host as in the reference's own GPU build).  Produces getMap() (CV_8UC1: 100 = L only, 50 = R only, 150 = overlap),
- * getOverlappedL()/getOverlappedR() (CV_8UC4, the inputs of pf_prepare_bidirectional), the un-smoothed blend (CV_32FC1) of
- * GenerateBlend :113-124 + countblend :148-191 (replaces countblend_Kernel, GPU/StitchTool_GPU.cu:10-66) and MergedDis.
- * Any output pointer may be NULL.  Images smaller than 200 px in their shorter side are rejected (the reference's search
- * step cols/200 would be 0 and its loop would not terminate).  HOST or DEVICE pointers, strides in bytes. */
+/* The stitching step around the flow path.
+ *
+ * pf_stitch_prepare replaces Stitchtools::prepare(colorImageL, colorImageR), CPU/StitchTool.cpp:7-36: MatchImages (:38-50),
+ * the overlap masking (:16-33) and GenerateBlend (:98-146) with countblend (:148-191; replaces the reference's own
+ * countblend_Kernel, GPU/StitchTool_GPU.cu:10-66, following the CPU path's sqrt(2) in double rather than that kernel's
+ * literal 1.4142).  Outputs: getMap() (CV_8UC1: 100 = L only, 50 = R only, 150 = overlap), getOverlappedL()/getOverlappedR()
+ * (CV_8UC4, the inputs of pf_prepare_bidirectional), the un-smoothed blend (CV_32FC1, GenerateBlend up to :131), MergedDis,
+ * and getBlend() = the blend after the block-wise in-place cv::blur on ROIs (:133-142, order-dependent: every block sees the
+ * blocks smoothed before it) and the final cv::blur (:143).  Any output pointer may be NULL.
+ * Sizes the reference itself cannot run are rejected with PF_ERR_INVALID_ARGUMENT: shorter side < 200 (its search step
+ * cols/200 would be 0 and countblend's loop would not terminate) and, when `blend` is requested, rows < 400 (cv::blur with
+ * the empty kernel rows/400).  HOST or DEVICE pointers, strides in bytes. */
 PF_API int pf_stitch_prepare(pf_engine* engine,
                              const void* image_l, size_t stride_l,
                              const void* image_r, size_t stride_r,
@@ -107,8 +112,35 @@ PF_API int pf_stitch_prepare(pf_engine* engine,
                              void* map_u8, size_t stride_map,
                              void* overlapped_l, size_t stride_ol,
                              void* overlapped_r, size_t stride_or,
-                             void* blend_raw, size_t stride_blend,
-                             void* merged_dis, size_t stride_dis);
+                             void* blend_raw, size_t stride_blend_raw,
+                             void* merged_dis, size_t stride_dis,
+                             void* blend, size_t stride_blend);
+
+/* Replaces Stitchtools::setMergedmiddle + Stitchtools::Gather(), CPU/StitchTool.cpp:52-96: composes FinalResult (CV_8UC4)
+ * from ImageL, ImageR, Mergedmiddle and Map.  The reference's unchecked map.at<uchar>(y +- i, x +- i) is reproduced as a
+ * flat index into the continuous rows x cols map; indices outside the allocation (undefined behaviour in the reference)
+ * match neither image. */
+PF_API int pf_stitch_gather(pf_engine* engine,
+                            const void* image_l, size_t stride_l,
+                            const void* image_r, size_t stride_r,
+                            const void* merged_middle, size_t stride_merged,
+                            const void* map_u8, size_t stride_map,
+                            int rows, int cols,
+                            void* final_result, size_t stride_out);
+
+/* One iteration of the reference driver's loop body, CPU/main.cpp:72-95, with every intermediate resident in HBM:
+ * Stitchtools::prepare -> NovelViewGeneratorAsymmetricFlow::prepare(OverlappedL, OverlappedR) -> setBlend(getBlend()) ->
+ * generateNovelView -> setMergedmiddle -> Gather -> getFinalResult().  final_result may be a DEVICE buffer that is passed
+ * back as image_r of the next iteration (the reference's colorImageR = FinalResult).  blend / merged_middle / map_u8 are
+ * optional outputs (NULL to skip). */
+PF_API int pf_stitch_iteration(pf_engine* engine,
+                               const void* image_l, size_t stride_l,
+                               const void* image_r, size_t stride_r,
+                               int rows, int cols,
+                               void* final_result, size_t stride_out,
+                               void* blend, size_t stride_blend,
+                               void* merged_middle, size_t stride_merged,
+                               void* map_u8, size_t stride_map);
 
 /* Pinned host memory for zero-staging transfers (optional; any host pointer is accepted by the calls above). */
 PF_API int pf_host_alloc(void** ptr, size_t bytes);
@@ -133,6 +165,8 @@ PF_API const char* pf_version(void);
 
 /* ---- diagnostic single-stage entry points (HOST pointers, contiguous arrays) --------------------------------
  * One kernel each, used by tests/ to localise a divergence to a stage.  Not a product API. */
+/* the smoothing of GenerateBlend (CPU/StitchTool.cpp:133-145) alone, in place on a dense HOST blend (rows x cols fp32) */
+PF_API int pf_stage_blend_smooth(pf_engine* engine, float* blend, const float* merged_dis, int rows, int cols);
 PF_API int pf_stage_frontend(const void* bgra, int rows, int cols, int pad, float* grey, float* alpha, int dh, int dw);
 PF_API int pf_stage_gauss5(const float* src, float* dst, int h, int w);
 PF_API int pf_stage_pyr_down(const float* src, int sh, int sw, float* dst, int dh, int dw);

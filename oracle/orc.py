@@ -262,3 +262,49 @@ def stitch_blend_raw(map_u8):
     if rc != 0:
         raise ValueError("image too small: the reference's search step cols/200 (rows/200) is 0")
     return blend, md
+
+
+def box_blur_rect(parent, x0, y0, rw, rh, k):
+    """cv::blur with a k x k kernel on the rectangle (x0, y0, rw, rh) of `parent` taken as a ROI (window pixels come
+    from the parent, reflect-101 beyond its edge); (0, 0, cols, rows) = cv::blur of the whole image."""
+    p, pp = _f(parent)
+    rows, cols = p.shape
+    out = np.empty((rh, rw), np.float32)
+    lib().orc_box_blur_rect(pp, rows, cols, x0, y0, rw, rh, k, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def stitch_blend_smooth(blend_raw, merged_dis):
+    """The smoothing of GenerateBlend (CPU/StitchTool.cpp:133-145) -> Blend."""
+    b = np.array(blend_raw, np.float32, order="C", copy=True)
+    md, pmd = _f(merged_dis)
+    rows, cols = b.shape
+    rc = lib().orc_stitch_blend_smooth(b.ctypes.data_as(C.c_void_p), pmd, rows, cols)
+    if rc != 0:
+        raise ValueError("image too small: rows/400 == 0 (cv::blur with an empty kernel) or search step 0")
+    return b
+
+
+def stitch_gather(imageL, imageR, merged, map_u8):
+    """Stitchtools::Gather (CPU/StitchTool.cpp:52-96) -> FinalResult."""
+    L, pl = _u(imageL)
+    R, pr = _u(imageR)
+    M, pm = _u(merged)
+    m, pmap = _u(map_u8)
+    rows, cols = m.shape
+    out = np.empty((rows, cols, 4), np.uint8)
+    lib().orc_stitch_gather(pl, pr, pm, pmap, rows, cols, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def stitch_iteration(imageL, imageR, max_percentage=20):
+    """One iteration of the reference driver (CPU/main.cpp:72-92): Stitchtools::prepare -> flow prepare -> setBlend ->
+    generateNovelView -> setMergedmiddle -> Gather.  Returns (FinalResult, dict of intermediates)."""
+    m, oL, oR = stitch_match_and_mask(imageL, imageR)
+    braw, md = stitch_blend_raw(m)
+    blend = stitch_blend_smooth(braw, md)
+    fLR, fRL = prepare_bidirectional(oL, oR, max_percentage)
+    merged = combine_novel_views(oL, oR, fLR, fRL, blend)
+    final = stitch_gather(imageL, imageR, merged, m)
+    return final, dict(map=m, overlappedL=oL, overlappedR=oR, blend_raw=braw, merged_dis=md, blend=blend,
+                       flowLtoR=fLR, flowRtoL=fRL, merged=merged)

@@ -832,3 +832,128 @@ ORC_API int orc_stitch_blend_raw(const uint8_t* map, int rows, int cols, float* 
     free(emap);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Section D: the rest of the stitching step around the flow path -- the blend smoothing of   */
+/* GenerateBlend (CPU/StitchTool.cpp:133-145) and Stitchtools::Gather (:52-96).               */
+/* ------------------------------------------------------------------------------------------ */
+
+/* cv::blur(src, dst, Size(k,k)) = normalized boxFilter on fp32 (anchor k/2, BORDER_REFLECT_101), arithmetic of
+ * cv2 4.13 scalar mode (pinned by tests/test_oracle_vs_cv2.py on data whose double sums are inexact):
+ *   row pass RowSum<float,double>: k <= 5 the k values are added left to right in double; k >= 6 a running sum --
+ *     s = sum of the first k values left to right, then s += (S[i+k] - S[i]) sliding along the row;
+ *   column pass ColumnSum<double,float>: SUM = first k-1 row sums added top to bottom (starting from 0), then per
+ *     output row s0 = SUM + newest; out = float(s0 * (1.0/(k*k))); SUM = s0 - oldest.
+ * Computes the rw x rh outputs whose top-left corner is (x0,y0) of the `parent` image (rows x cols).  Pixels outside
+ * that rectangle are read from the parent; only beyond the parent's own edge are they reflect-101 extrapolated --
+ * OpenCV's semantics for filtering a Mat that is a ROI of a bigger Mat (no BORDER_ISOLATED), which is what
+ * GenerateBlend does block by block.  With (x0,y0,rw,rh) = (0,0,cols,rows) this is plain cv::blur on the whole image.
+ * `out` is dense rw x rh and must not alias parent. */
+ORC_API void orc_box_blur_rect(const float* parent, int rows, int cols, int x0, int y0, int rw, int rh, int k, float* out) {
+    const int a = k / 2;
+    const int nr = rh + k - 1, nc = rw + k - 1;
+    double* rs = (double*)malloc((size_t)nr * rw * sizeof(double));
+    double* S = (double*)malloc((size_t)nc * sizeof(double));
+    double* SUM = (double*)calloc((size_t)rw, sizeof(double));
+    for (int r = 0; r < nr; ++r) {
+        const float* src = parent + (size_t)reflect101(y0 - a + r, rows) * cols;
+        for (int c = 0; c < nc; ++c) S[c] = (double)src[reflect101(x0 - a + c, cols)];
+        double* D = rs + (size_t)r * rw;
+        if (k <= 5) {
+            for (int i = 0; i < rw; ++i) {
+                double s = S[i];
+                for (int j = 1; j < k; ++j) s += S[i + j];
+                D[i] = s;
+            }
+        } else {
+            double s = 0;
+            for (int i = 0; i < k; ++i) s += S[i];
+            D[0] = s;
+            for (int i = 0; i + 1 < rw; ++i) {
+                s += S[i + k] - S[i];
+                D[i + 1] = s;
+            }
+        }
+    }
+    const double scale = 1.0 / (double)(k * k);
+    for (int r = 0; r < k - 1; ++r)
+        for (int i = 0; i < rw; ++i) SUM[i] += rs[(size_t)r * rw + i];
+    for (int y = 0; y < rh; ++y) {
+        const double* Sp = rs + (size_t)(y + k - 1) * rw;
+        const double* Sm = rs + (size_t)y * rw;
+        for (int i = 0; i < rw; ++i) {
+            double s0 = SUM[i] + Sp[i];
+            out[(size_t)y * rw + i] = (float)(s0 * scale);
+            s0 -= Sm[i];
+            SUM[i] = s0;
+        }
+    }
+    free(rs); free(S); free(SUM);
+}
+
+/* The smoothing of GenerateBlend (CPU/StitchTool.cpp:133-145), in place on blend (rows x cols):
+ *   step = min(cols,rows)/200; for every step x step block (raster order, blocks with y+step < rows, x+step < cols)
+ *   whose MergedDis(y,x) > step: blur(blockROI, blockROI, Size(rows/130, rows/130)) -- each block is filtered as a ROI of
+ *   the image being modified, so its window sees the blocks already smoothed above / to the left and the still raw ones
+ *   below / to the right; finally blur(blend, blend, Size(rows/400, rows/400)).
+ * Returns 1 when the reference itself cannot run (rows < 400: cv::blur with a 0 x 0 kernel throws; step < 1: endless loop). */
+ORC_API int orc_stitch_blend_smooth(float* blend, const float* merged_dis, int rows, int cols) {
+    const int step = (cols <= rows) ? cols / 200 : rows / 200;
+    const int k1 = rows / 130, k2 = rows / 400;
+    if (step < 1 || k2 < 1) return 1;
+    float* tmp = (float*)malloc((size_t)step * step * sizeof(float));
+    for (int y = 0; y + step < rows; y += step)
+        for (int x = 0; x + step < cols; x += step)
+            if (merged_dis[(size_t)y * cols + x] > step) {
+                orc_box_blur_rect(blend, rows, cols, x, y, step, step, k1, tmp);
+                for (int r = 0; r < step; ++r) memcpy(blend + (size_t)(y + r) * cols + x, tmp + (size_t)r * step, (size_t)step * sizeof(float));
+            }
+    free(tmp);
+    float* full = (float*)malloc((size_t)rows * cols * sizeof(float));
+    orc_box_blur_rect(blend, rows, cols, 0, 0, cols, rows, k2, full);
+    memcpy(blend, full, (size_t)rows * cols * sizeof(float));
+    free(full);
+    return 0;
+}
+
+/* Stitchtools::Gather (CPU/StitchTool.cpp:52-96).  map = Map + (alpha(Mergedmiddle) > 0 ? 75 : 0) (u8);
+ * 100 -> ImageL, 50 -> ImageR, 225/125/175 -> Mergedmiddle, 0 -> (0,0,0,0), 150 (overlap the merged view left empty) ->
+ * search the 8 directions at distance i = 1..99: the first i with a 100 among the 8 samples takes ImageL, else with a 50
+ * ImageR, else the pixel is (0,0,0,255); any other code (75) keeps the zero the result was initialised with.
+ * The reference indexes map.at<uchar>(y +- i, x +- i) without bounds checks: on its continuous rows x cols Mat that
+ * reads the byte at flat index (y +- i)*cols + (x +- i), i.e. wraps into the neighbouring row; this restatement does
+ * the same for flat indices inside the allocation and treats indices outside it (undefined behaviour in the reference)
+ * as matching neither 100 nor 50. */
+ORC_API void orc_stitch_gather(const uint8_t* L, const uint8_t* R, const uint8_t* merged, const uint8_t* map0, int rows, int cols,
+                               uint8_t* result) {
+    const long n = (long)rows * cols;
+    uint8_t* map = (uint8_t*)malloc((size_t)n);
+    for (long p = 0; p < n; ++p) {
+        const int v = map0[p] + (merged[p * 4 + 3] > 0 ? 75 : 0);
+        map[p] = (uint8_t)(v > 255 ? 255 : v);
+    }
+#define GM(yy, xx) (((long)(yy) * cols + (xx)) >= 0 && ((long)(yy) * cols + (xx)) < n ? map[(long)(yy) * cols + (xx)] : 0)
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            const long p = (long)y * cols + x;
+            uint8_t* o = result + p * 4;
+            const int m = map[p];
+            o[0] = o[1] = o[2] = o[3] = 0;
+            if (m == 100) memcpy(o, L + p * 4, 4);
+            else if (m == 50) memcpy(o, R + p * 4, 4);
+            else if (m == 225 || m == 125 || m == 175) memcpy(o, merged + p * 4, 4);
+            else if (m == 150) {
+                for (int i = 1; i < 100; i++) {
+                    const int s[8] = {GM(y, x + i), GM(y, x - i), GM(y + i, x), GM(y - i, x),
+                                      GM(y - i, x - i), GM(y - i, x + i), GM(y + i, x - i), GM(y + i, x + i)};
+                    int has100 = 0, has50 = 0;
+                    for (int q = 0; q < 8; ++q) { has100 |= s[q] == 100; has50 |= s[q] == 50; }
+                    if (has100) { memcpy(o, L + p * 4, 4); break; }
+                    else if (has50) { memcpy(o, R + p * 4, 4); break; }
+                    else { o[0] = o[1] = o[2] = 0; o[3] = 255; }
+                }
+            }
+        }
+#undef GM
+    free(map);
+}

@@ -23,7 +23,9 @@ SIGNATURES = {
                                             C.POINTER(_vp), _sz, C.POINTER(_vp), _sz]),
     "pf_combine_novel_views": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
     "pf_novel_view": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz]),
-    "pf_stitch_prepare": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "pf_stitch_prepare": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "pf_stitch_gather": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
+    "pf_stitch_iteration": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "pf_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "pf_host_free": (_i, [_vp]),
     "pf_kernel_launch_count": (C.c_uint64, []),
@@ -44,6 +46,7 @@ SIGNATURES = {
     "pf_stage_sweep": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "pf_stage_upsample_cubic": (_i, [_vp, _i, _i, _vp, _i, _i]),
     "pf_stage_tail": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pf_stage_blend_smooth": (_i, [_vp, _vp, _vp, _i, _i]),
     "pf_stage_initial_flow": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
 }
 

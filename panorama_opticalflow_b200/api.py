@@ -250,17 +250,20 @@ class NovelViewGeneratorAsymmetricFlow(NovelViewGenerator):
 
 
 class Stitchtools:
-    """Stitchtools (CPU/StitchTool.hpp:21-61) -- the part of prepare() that runs on the B200: canvas map, overlap masking
-    and the un-smoothed blend map (MatchImages, GenerateBlend up to :131, countblend).  The block-wise blur that follows
-    in GenerateBlend (CPU/StitchTool.cpp:133-145) is not implemented here."""
+    """Stitchtools (CPU/StitchTool.hpp:21-61) on the B200: prepare() (MatchImages, overlap masking, GenerateBlend with
+    countblend and the blend smoothing), setMergedmiddle() + Gather(), and the getters of the reference.  Member names are
+    the reference's (ImageL, ImageR, Blend, OverlappedL, OverlappedR, Mergedmiddle, Map, FinalResult, MergedDis)."""
 
     def __init__(self, flowAlg=None, device=-1):
         self._own = flowAlg is None
         self._alg = makeOpticalFlowByName("pixflow_low", device) if flowAlg is None else flowAlg
         self.ImageL = self.ImageR = None
-        self.Map = self.OverlappedL = self.OverlappedR = self.BlendUnsmoothed = self.MergedDis = None
+        self.Map = self.OverlappedL = self.OverlappedR = self.Blend = self.BlendUnsmoothed = self.MergedDis = None
+        self.Mergedmiddle = self.FinalResult = None
 
     def prepare(self, colorImageL, colorImageR):
+        """CPU/StitchTool.cpp:7-36.  Raises PixFlowError for sizes the reference itself cannot run (rows < 400 or a shorter
+        side < 200)."""
         self.ImageL = np.array(colorImageL, copy=True)
         self.ImageR = np.array(colorImageR, copy=True)
         kl, pl, sl, rows, cols = _view(self.ImageL, np.uint8, 4, "colorImageL")
@@ -272,10 +275,39 @@ class Stitchtools:
         self.OverlappedR = np.empty((rows, cols, 4), np.uint8)
         self.BlendUnsmoothed = np.empty((rows, cols), np.float32)
         self.MergedDis = np.empty((rows, cols), np.float32)
+        self.Blend = np.empty((rows, cols), np.float32)
         p = lambda a: C.c_void_p(a.ctypes.data)
         _lib.check(self._alg._lib.pf_stitch_prepare(
             self._alg._h, pl, sl, pr, sr, rows, cols, p(self.Map), cols, p(self.OverlappedL), cols * 4,
-            p(self.OverlappedR), cols * 4, p(self.BlendUnsmoothed), cols * 4, p(self.MergedDis), cols * 4))
+            p(self.OverlappedR), cols * 4, p(self.BlendUnsmoothed), cols * 4, p(self.MergedDis), cols * 4,
+            p(self.Blend), cols * 4))
+
+    def setMergedmiddle(self, image):
+        self.Mergedmiddle = np.array(image, copy=True)
+
+    def Gather(self):
+        """CPU/StitchTool.cpp:52-96 -> FinalResult"""
+        if self.Map is None or self.Mergedmiddle is None:
+            raise RuntimeError("Gather() needs prepare() and setMergedmiddle() first")
+        rows, cols = self.Map.shape
+        kl, pl, sl, _, _ = _view(self.ImageL, np.uint8, 4, "ImageL")
+        kr, pr, sr, _, _ = _view(self.ImageR, np.uint8, 4, "ImageR")
+        km, pm, sm, r1, c1 = _view(self.Mergedmiddle, np.uint8, 4, "Mergedmiddle")
+        if (rows, cols) != (r1, c1):
+            raise ValueError("Mergedmiddle must have the size of the canvas")
+        self.FinalResult = np.empty((rows, cols, 4), np.uint8)
+        _lib.check(self._alg._lib.pf_stitch_gather(
+            self._alg._h, pl, sl, pr, sr, pm, sm, C.c_void_p(self.Map.ctypes.data), cols, rows, cols,
+            C.c_void_p(self.FinalResult.ctypes.data), cols * 4))
+
+    def getImageL(self):
+        return self.ImageL
+
+    def getImageR(self):
+        return self.ImageR
+
+    def getBlend(self):
+        return self.Blend
 
     def getMap(self):
         return self.Map
@@ -286,9 +318,49 @@ class Stitchtools:
     def getOverlappedR(self):
         return self.OverlappedR
 
+    def getFinalResult(self):
+        return self.FinalResult
+
     def getBlendUnsmoothed(self):
+        """GenerateBlend's map before its smoothing (CPU/StitchTool.cpp:113-124); not a member of the reference class"""
         return self.BlendUnsmoothed
 
     def close(self):
         if self._own:
             self._alg.close()
+
+
+def stitch_iteration(flowAlg, colorImageL, colorImageR, out=None, want_intermediates=False):
+    """One pass of the loop body of the reference driver (CPU/main.cpp:72-95) as ONE call, every intermediate resident in
+    HBM: Stitchtools::prepare -> NovelViewGeneratorAsymmetricFlow::prepare -> setBlend -> generateNovelView ->
+    setMergedmiddle -> Gather.  Images may be numpy arrays or CUDA tensors; `out` may be a CUDA uint8 tensor (rows, cols, 4)
+    that is fed back as colorImageR of the next iteration.  Returns FinalResult (and a dict of Blend / Mergedmiddle / Map)."""
+    kl, pl, sl, rows, cols = _view(colorImageL, np.uint8, 4, "colorImageL")
+    kr, pr, sr, r1, c1 = _view(colorImageR, np.uint8, 4, "colorImageR")
+    if (rows, cols) != (r1, c1):
+        raise ValueError("colorImageL and colorImageR must have the same size")
+    if out is None:
+        out = np.empty((rows, cols, 4), np.uint8)
+    ko, po, so, r2, c2 = _view(out, np.uint8, 4, "out")
+    if (rows, cols) != (r2, c2) or (not _is_device_tensor(out) and ko is not out):
+        raise ValueError("out must be a dense (rows, cols, 4) uint8 buffer of the canvas size")
+    null = C.c_void_p(None)
+    extra = {}
+    args = [null, 0, null, 0, null, 0]
+    if want_intermediates:
+        extra = dict(Blend=np.empty((rows, cols), np.float32), Mergedmiddle=np.empty((rows, cols, 4), np.uint8),
+                     Map=np.empty((rows, cols), np.uint8))
+        args = [C.c_void_p(extra["Blend"].ctypes.data), cols * 4, C.c_void_p(extra["Mergedmiddle"].ctypes.data), cols * 4,
+                C.c_void_p(extra["Map"].ctypes.data), cols]
+    _lib.check(flowAlg._lib.pf_stitch_iteration(flowAlg._h, pl, sl, pr, sr, rows, cols, po, so, *args))
+    return (out, extra) if want_intermediates else out
+
+
+def _blend_smooth_for_tests(flowAlg, blend_raw, merged_dis):
+    """The smoothing of GenerateBlend (CPU/StitchTool.cpp:133-145) alone, on caller-supplied values (diagnostic entry point
+    pf_stage_blend_smooth; used by the parity tests to drive the box filters with adversarial data)."""
+    b = np.array(blend_raw, np.float32, order="C", copy=True)
+    md = np.ascontiguousarray(merged_dis, np.float32)
+    rows, cols = b.shape
+    _lib.check(flowAlg._lib.pf_stage_blend_smooth(flowAlg._h, C.c_void_p(b.ctypes.data), C.c_void_p(md.ctypes.data), rows, cols))
+    return b

@@ -5,6 +5,7 @@
 // coarse-to-fine loop without any host round trip; the two directions L->R and R->L share the front end,
 // pyramids and gradients (the reference recomputes them per direction, CPU/OpticalFlow.cpp:130-139).
 #include <atomic>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -500,8 +501,14 @@ int pf_engine_create(const char* name, int device, pf_engine** out) {
     return PF_OK;
 }
 
+void release_stitch_bufs(pf_engine* e);
+
 void pf_engine_destroy(pf_engine* e) {
     if (!e) return;
+    {
+        DeviceGuard g(e->device);
+        release_stitch_bufs(e);
+    }
     {
         std::lock_guard<std::mutex> cg(g_capture_mu);
         DeviceGuard g(e->device);
@@ -684,18 +691,10 @@ int pf_combine_novel_views(pf_engine* e, const void* L, size_t sl, const void* R
     return PF_OK;
 }
 
-int pf_novel_view(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, const void* blend, size_t sb,
-                  int rows, int cols, void* out, size_t so, void* lr, size_t slr, void* rl, size_t srl) {
-    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+// body of pf_novel_view; e->mu held by the caller, arguments already checked
+static int novel_view_locked(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, const void* blend, size_t sb,
+                             int rows, int cols, void* out, size_t so, void* lr, size_t slr, void* rl, size_t srl) {
     int rc;
-    if ((rc = check_image_args(L, sl, rows, cols, 4, "imageL")) != PF_OK) return rc;
-    if ((rc = check_image_args(R, sr, rows, cols, 4, "imageR")) != PF_OK) return rc;
-    if ((rc = check_image_args(blend, sb, rows, cols, 4, "blend")) != PF_OK) return rc;
-    if ((rc = check_image_args(out, so, rows, cols, 4, "out")) != PF_OK) return rc;
-    if (lr && (rc = check_image_args(lr, slr, rows, cols, 8, "flowLtoR")) != PF_OK) return rc;
-    if (rl && (rc = check_image_args(rl, srl, rows, cols, 8, "flowRtoL")) != PF_OK) return rc;
-    std::lock_guard<std::mutex> lk(e->mu);
-    DeviceGuard g(e->device);
     Workspace* w;
     const int pad = cols / 20;
     if ((rc = e->workspace(0, rows, cols, pad, &w)) != PF_OK) return rc;
@@ -713,46 +712,204 @@ int pf_novel_view(pf_engine* e, const void* L, size_t sl, const void* R, size_t 
     return collect_sweep_timing(e, used);
 }
 
+int pf_novel_view(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, const void* blend, size_t sb,
+                  int rows, int cols, void* out, size_t so, void* lr, size_t slr, void* rl, size_t srl) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    int rc;
+    if ((rc = check_image_args(L, sl, rows, cols, 4, "imageL")) != PF_OK) return rc;
+    if ((rc = check_image_args(R, sr, rows, cols, 4, "imageR")) != PF_OK) return rc;
+    if ((rc = check_image_args(blend, sb, rows, cols, 4, "blend")) != PF_OK) return rc;
+    if ((rc = check_image_args(out, so, rows, cols, 4, "out")) != PF_OK) return rc;
+    if (lr && (rc = check_image_args(lr, slr, rows, cols, 8, "flowLtoR")) != PF_OK) return rc;
+    if (rl && (rc = check_image_args(rl, srl, rows, cols, 8, "flowRtoL")) != PF_OK) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    return novel_view_locked(e, L, sl, R, sr, blend, sb, rows, cols, out, so, lr, slr, rl, srl);
+}
+
+// ---- the stitching step around the flow path -----------------------------------------
+
+// device buffers of the stitching entry points, kept across calls (a 36 Mpx canvas needs ~1.7 GB of them)
+struct StitchBufs {
+    int rows = 0, cols = 0;
+    uint8_t *L = nullptr, *R = nullptr, *map = nullptr, *oL = nullptr, *oR = nullptr, *merged = nullptr, *gmap = nullptr, *result = nullptr;
+    float *braw = nullptr, *mdis = nullptr, *blend = nullptr;
+    void* scratch = nullptr;
+    cudaStream_t st = nullptr;                 // the stitching kernels' own (non-blocking) stream
+    void release() {
+        std::lock_guard<std::mutex> cg(g_capture_mu);
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
+        cudaFree(L); cudaFree(R); cudaFree(map); cudaFree(oL); cudaFree(oR); cudaFree(merged); cudaFree(gmap); cudaFree(result);
+        cudaFree(braw); cudaFree(mdis); cudaFree(blend); cudaFree(scratch);
+        L = R = map = oL = oR = merged = gmap = result = nullptr; braw = mdis = blend = nullptr; scratch = nullptr;
+        rows = cols = 0;
+    }
+    int ensure(int r, int c) {
+        if (r == rows && c == cols) return PF_OK;
+        release();
+        std::lock_guard<std::mutex> cg(g_capture_mu);
+        const size_t n = (size_t)r * c;
+        PF_CUDA(cudaMalloc(&L, n * 4)); PF_CUDA(cudaMalloc(&R, n * 4)); PF_CUDA(cudaMalloc(&map, n));
+        PF_CUDA(cudaMalloc(&oL, n * 4)); PF_CUDA(cudaMalloc(&oR, n * 4)); PF_CUDA(cudaMalloc(&merged, n * 4));
+        PF_CUDA(cudaMalloc(&gmap, n)); PF_CUDA(cudaMalloc(&result, n * 4));
+        PF_CUDA(cudaMalloc(&braw, n * 4)); PF_CUDA(cudaMalloc(&mdis, n * 4)); PF_CUDA(cudaMalloc(&blend, n * 4));
+        const size_t sb = pf::stitch_smooth_scratch_bytes(r, c);
+        PF_CUDA(cudaMalloc(&scratch, sb ? sb : 16));
+        PF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        rows = r; cols = c;
+        return PF_OK;
+    }
+};
+static std::mutex g_stitch_mu;
+static std::map<pf_engine*, StitchBufs> g_stitch_bufs;      // released by pf_engine_destroy
+
+static StitchBufs& stitch_bufs(pf_engine* e) {
+    std::lock_guard<std::mutex> lk(g_stitch_mu);
+    return g_stitch_bufs[e];
+}
+void release_stitch_bufs(pf_engine* e) {
+    std::lock_guard<std::mutex> lk(g_stitch_mu);
+    auto it = g_stitch_bufs.find(e);
+    if (it != g_stitch_bufs.end()) { it->second.release(); g_stitch_bufs.erase(it); }
+}
+
+static int stitch_size_check(int rows, int cols, bool need_smooth) {
+    if (((cols <= rows) ? cols / 200 : rows / 200) < 1)
+        return fail(PF_ERR_INVALID_ARGUMENT, "image too small for Stitchtools::countblend (shorter side < 200)");
+    if (need_smooth) {
+        int step, k1, k2; size_t smem;
+        const int g = pf::stitch_smooth_geometry(rows, cols, &step, &k1, &k2, &smem);
+        if (g == 1) return fail(PF_ERR_INVALID_ARGUMENT, "image too small for GenerateBlend's blur (rows < 400: cv::blur kernel rows/400 is empty)");
+        if (g == 2) return fail(PF_ERR_INVALID_ARGUMENT, "image shape not supported by the blend smoothing (window exceeds shared memory)");
+    }
+    return PF_OK;
+}
+
+// Stitchtools::prepare on device buffers held in sb (inputs already in sb.L/sb.R or given in place); asynchronous on st
+static int stitch_prepare_dev(StitchBufs& sb, const uint8_t* dL, size_t sl, const uint8_t* dR, size_t sr, int rows, int cols,
+                              bool smooth, cudaStream_t st) {
+    const size_t c1 = (size_t)cols, c4 = (size_t)cols * 4;
+    pf::launch_stitch_match_mask(dL, sl, dR, sr, rows, cols, sb.map, c1, sb.oL, c4, sb.oR, c4, st);
+    pf::launch_stitch_blend_raw(sb.map, c1, rows, cols, sb.braw, c4, sb.mdis, c4, st);
+    LAUNCHED(2);
+    if (smooth) {
+        PF_CUDA(cudaMemcpyAsync(sb.blend, sb.braw, (size_t)rows * c4, cudaMemcpyDeviceToDevice, st));
+        const int n = pf::launch_stitch_blend_smooth(sb.blend, c4, sb.mdis, c4, rows, cols, sb.scratch, st);
+        if (n == 0) return fail(PF_ERR_INVALID_ARGUMENT, "blend smoothing: unsupported image shape");
+        LAUNCHED(n);
+    }
+    PF_CUDA(cudaGetLastError());
+    return PF_OK;
+}
+
+static int stage_u8(const void* src, size_t stride, int rows, size_t row_bytes, uint8_t* dev, const uint8_t** p, size_t* ps, cudaStream_t st) {
+    if (is_device_ptr(src)) { *p = (const uint8_t*)src; *ps = stride; return PF_OK; }
+    PF_CUDA(cudaMemcpy2DAsync(dev, row_bytes, src, stride, row_bytes, rows, cudaMemcpyHostToDevice, st));
+    *p = dev; *ps = row_bytes;
+    return PF_OK;
+}
+static int copy_out(void* user, size_t ustride, const void* dev, size_t row_bytes, int rows, cudaStream_t st) {
+    if (!user) return PF_OK;
+    PF_CUDA(cudaMemcpy2DAsync(user, ustride, dev, row_bytes, row_bytes, rows, cudaMemcpyDefault, st));
+    return PF_OK;
+}
+
 int pf_stitch_prepare(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, int rows, int cols,
-                      void* map, size_t sm, void* oL, size_t sol, void* oR, size_t sor, void* blend, size_t sb, void* mdis, size_t sd) {
+                      void* map, size_t sm, void* oL, size_t sol, void* oR, size_t sor, void* braw, size_t sbr, void* mdis, size_t sd,
+                      void* blend, size_t sbl) {
     if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
     int rc;
     if ((rc = check_image_args(L, sl, rows, cols, 4, "colorImageL")) != PF_OK) return rc;
     if ((rc = check_image_args(R, sr, rows, cols, 4, "colorImageR")) != PF_OK) return rc;
-    if (((cols <= rows) ? cols / 200 : rows / 200) < 1)
-        return fail(PF_ERR_INVALID_ARGUMENT, "image too small for Stitchtools::countblend (shorter side < 200)");
+    if ((rc = stitch_size_check(rows, cols, blend != nullptr)) != PF_OK) return rc;
     if (map && sm < (size_t)cols) return fail(PF_ERR_INVALID_ARGUMENT, "map stride < cols");
     if (oL && (rc = check_image_args(oL, sol, rows, cols, 4, "OverlappedL")) != PF_OK) return rc;
     if (oR && (rc = check_image_args(oR, sor, rows, cols, 4, "OverlappedR")) != PF_OK) return rc;
-    if (blend && (rc = check_image_args(blend, sb, rows, cols, 4, "blend")) != PF_OK) return rc;
+    if (braw && (rc = check_image_args(braw, sbr, rows, cols, 4, "blend (un-smoothed)")) != PF_OK) return rc;
     if (mdis && (rc = check_image_args(mdis, sd, rows, cols, 4, "MergedDis")) != PF_OK) return rc;
+    if (blend && (rc = check_image_args(blend, sbl, rows, cols, 4, "Blend")) != PF_OK) return rc;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard g(e->device);
-    // device staging (dense) for whatever lives on the host
-    DevBuf dL, dR, dM, dOL, dOR, dB, dD;
-    const size_t n = (size_t)rows * cols;
-    const uint8_t* pL; const uint8_t* pR; size_t psl, psr;
-    if (is_device_ptr(L)) { pL = (const uint8_t*)L; psl = sl; }
-    else { RC(dL.alloc(n * 4)); PF_CUDA(cudaMemcpy2D(dL.p, (size_t)cols * 4, L, sl, (size_t)cols * 4, rows, cudaMemcpyHostToDevice)); pL = dL.as<uint8_t>(); psl = (size_t)cols * 4; }
-    if (is_device_ptr(R)) { pR = (const uint8_t*)R; psr = sr; }
-    else { RC(dR.alloc(n * 4)); PF_CUDA(cudaMemcpy2D(dR.p, (size_t)cols * 4, R, sr, (size_t)cols * 4, rows, cudaMemcpyHostToDevice)); pR = dR.as<uint8_t>(); psr = (size_t)cols * 4; }
-    struct Out { void* user; size_t ustride; DevBuf* buf; size_t elem; uint8_t* dev; size_t dstride; };
-    Out outs[5] = {{map, sm, &dM, 1, nullptr, 0}, {oL, sol, &dOL, 4, nullptr, 0}, {oR, sor, &dOR, 4, nullptr, 0},
-                   {blend, sb, &dB, 4, nullptr, 0}, {mdis, sd, &dD, 4, nullptr, 0}};
-    for (auto& o : outs) {
-        if (o.user && is_device_ptr(o.user)) { o.dev = (uint8_t*)o.user; o.dstride = o.ustride; }
-        else { RC(o.buf->alloc(n * o.elem)); o.dev = o.buf->as<uint8_t>(); o.dstride = (size_t)cols * o.elem; }
-    }
-    pf::launch_stitch_match_mask(pL, psl, pR, psr, rows, cols, outs[0].dev, outs[0].dstride, outs[1].dev, outs[1].dstride,
-                                 outs[2].dev, outs[2].dstride, 0);
-    pf::launch_stitch_blend_raw(outs[0].dev, outs[0].dstride, rows, cols, (float*)outs[3].dev, outs[3].dstride,
-                                (float*)outs[4].dev, outs[4].dstride, 0);
+    StitchBufs& sb = stitch_bufs(e);
+    RC(sb.ensure(rows, cols));
+    cudaStream_t st = sb.st;
+    const size_t c4 = (size_t)cols * 4;
+    const uint8_t *pL, *pR; size_t psl, psr;
+    RC(stage_u8(L, sl, rows, c4, sb.L, &pL, &psl, st));
+    RC(stage_u8(R, sr, rows, c4, sb.R, &pR, &psr, st));
+    RC(stitch_prepare_dev(sb, pL, psl, pR, psr, rows, cols, blend != nullptr, st));
+    RC(copy_out(map, sm, sb.map, (size_t)cols, rows, st));
+    RC(copy_out(oL, sol, sb.oL, c4, rows, st));
+    RC(copy_out(oR, sor, sb.oR, c4, rows, st));
+    RC(copy_out(braw, sbr, sb.braw, c4, rows, st));
+    RC(copy_out(mdis, sd, sb.mdis, c4, rows, st));
+    RC(copy_out(blend, sbl, sb.blend, c4, rows, st));
+    PF_CUDA(cudaStreamSynchronize(st));
+    return PF_OK;
+}
+
+int pf_stitch_gather(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, const void* merged, size_t smg,
+                     const void* map, size_t sm, int rows, int cols, void* out, size_t so) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    int rc;
+    if ((rc = check_image_args(L, sl, rows, cols, 4, "ImageL")) != PF_OK) return rc;
+    if ((rc = check_image_args(R, sr, rows, cols, 4, "ImageR")) != PF_OK) return rc;
+    if ((rc = check_image_args(merged, smg, rows, cols, 4, "Mergedmiddle")) != PF_OK) return rc;
+    if ((rc = check_image_args(out, so, rows, cols, 4, "FinalResult")) != PF_OK) return rc;
+    if (!map || sm < (size_t)cols) return fail(PF_ERR_INVALID_ARGUMENT, "Map is NULL or its stride < cols");
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    StitchBufs& sb = stitch_bufs(e);
+    RC(sb.ensure(rows, cols));
+    cudaStream_t st = sb.st;
+    const size_t c4 = (size_t)cols * 4;
+    const uint8_t *pL, *pR, *pM, *pMap; size_t psl, psr, psm, psmap;
+    RC(stage_u8(L, sl, rows, c4, sb.L, &pL, &psl, st));
+    RC(stage_u8(R, sr, rows, c4, sb.R, &pR, &psr, st));
+    RC(stage_u8(merged, smg, rows, c4, sb.merged, &pM, &psm, st));
+    RC(stage_u8(map, sm, rows, (size_t)cols, sb.map, &pMap, &psmap, st));
+    pf::launch_stitch_gather(pL, psl, pR, psr, pM, psm, pMap, psmap, rows, cols, sb.gmap, sb.result, c4, st);
     LAUNCHED(2);
     PF_CUDA(cudaGetLastError());
-    PF_CUDA(cudaDeviceSynchronize());
-    for (auto& o : outs)
-        if (o.user && !is_device_ptr(o.user))
-            PF_CUDA(cudaMemcpy2D(o.user, o.ustride, o.dev, o.dstride, (size_t)cols * o.elem, rows, cudaMemcpyDeviceToHost));
+    RC(copy_out(out, so, sb.result, c4, rows, st));
+    PF_CUDA(cudaStreamSynchronize(st));
+    return PF_OK;
+}
+
+int pf_stitch_iteration(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, int rows, int cols,
+                        void* out, size_t so, void* blend, size_t sbl, void* merged, size_t smg, void* map, size_t sm) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    int rc;
+    if ((rc = check_image_args(L, sl, rows, cols, 4, "colorImageL")) != PF_OK) return rc;
+    if ((rc = check_image_args(R, sr, rows, cols, 4, "colorImageR")) != PF_OK) return rc;
+    if ((rc = check_image_args(out, so, rows, cols, 4, "FinalResult")) != PF_OK) return rc;
+    if ((rc = stitch_size_check(rows, cols, true)) != PF_OK) return rc;
+    if (blend && (rc = check_image_args(blend, sbl, rows, cols, 4, "Blend")) != PF_OK) return rc;
+    if (merged && (rc = check_image_args(merged, smg, rows, cols, 4, "Mergedmiddle")) != PF_OK) return rc;
+    if (map && sm < (size_t)cols) return fail(PF_ERR_INVALID_ARGUMENT, "map stride < cols");
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    StitchBufs& sb = stitch_bufs(e);
+    RC(sb.ensure(rows, cols));
+    cudaStream_t st = sb.st;
+    const size_t c4 = (size_t)cols * 4;
+    const uint8_t *pL, *pR; size_t psl, psr;
+    RC(stage_u8(L, sl, rows, c4, sb.L, &pL, &psl, st));
+    RC(stage_u8(R, sr, rows, c4, sb.R, &pR, &psr, st));
+    // Stitchtools::prepare (CPU/main.cpp:72-73)
+    RC(stitch_prepare_dev(sb, pL, psl, pR, psr, rows, cols, true, st));
+    PF_CUDA(cudaStreamSynchronize(st));
+    // NovelViewGeneratorAsymmetricFlow::prepare + setBlend + generateNovelView (:82-89), everything device-resident
+    RC(novel_view_locked(e, sb.oL, c4, sb.oR, c4, sb.blend, c4, rows, cols, sb.merged, c4, nullptr, 0, nullptr, 0));
+    // setMergedmiddle + Gather (:93-95)
+    pf::launch_stitch_gather(pL, psl, pR, psr, sb.merged, c4, sb.map, (size_t)cols, rows, cols, sb.gmap, sb.result, c4, st);
+    LAUNCHED(2);
+    PF_CUDA(cudaGetLastError());
+    RC(copy_out(out, so, sb.result, c4, rows, st));
+    RC(copy_out(blend, sbl, sb.blend, c4, rows, st));
+    RC(copy_out(merged, smg, sb.merged, c4, rows, st));
+    RC(copy_out(map, sm, sb.map, (size_t)cols, rows, st));
+    PF_CUDA(cudaStreamSynchronize(st));
     return PF_OK;
 }
 
@@ -780,6 +937,26 @@ int pf_host_free(void* p) {
 // ---- diagnostic single-stage entry points ---------------------------------------------------------------
 
 extern "C" {
+
+int pf_stage_blend_smooth(pf_engine* e, float* blend, const float* mdis, int rows, int cols) {
+    if (!e || !blend || !mdis) return fail(PF_ERR_INVALID_ARGUMENT, "NULL argument");
+    int rc;
+    if ((rc = stitch_size_check(rows, cols, true)) != PF_OK) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    StitchBufs& sb = stitch_bufs(e);
+    RC(sb.ensure(rows, cols));
+    const size_t n = (size_t)rows * cols * 4;
+    PF_CUDA(cudaMemcpyAsync(sb.blend, blend, n, cudaMemcpyHostToDevice, sb.st));
+    PF_CUDA(cudaMemcpyAsync(sb.mdis, mdis, n, cudaMemcpyHostToDevice, sb.st));
+    const int nk = pf::launch_stitch_blend_smooth(sb.blend, (size_t)cols * 4, sb.mdis, (size_t)cols * 4, rows, cols, sb.scratch, sb.st);
+    if (nk == 0) return fail(PF_ERR_INVALID_ARGUMENT, "blend smoothing: unsupported image shape");
+    LAUNCHED(nk);
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaMemcpyAsync(blend, sb.blend, n, cudaMemcpyDeviceToHost, sb.st));
+    PF_CUDA(cudaStreamSynchronize(sb.st));
+    return PF_OK;
+}
 
 int pf_stage_frontend(const void* bgra, int rows, int cols, int pad, float* grey, float* alpha, int dh, int dw) {
     DevBuf in, g, a;

@@ -88,6 +88,17 @@ void launch_stitch_match_mask(const uint8_t* L, size_t strideL, const uint8_t* R
 void launch_stitch_blend_raw(const uint8_t* map, size_t strideM, int rows, int cols, float* blend, size_t strideB,
                              float* mdis, size_t strideD, cudaStream_t st);
 
+// the smoothing of GenerateBlend (:133-145), in place on blend; scratch = stitch_smooth_scratch_bytes(rows, cols) device bytes.
+// stitch_smooth_geometry: 0 ok, 1 the reference itself cannot run this size (rows < 400 or shorter side < 200), 2 unsupported.
+int stitch_smooth_geometry(int rows, int cols, int* step, int* k1, int* k2, size_t* smem_bytes);
+size_t stitch_smooth_scratch_bytes(int rows, int cols);
+int launch_stitch_blend_smooth(float* blend, size_t strideB, const float* mdis, size_t strideD, int rows, int cols,
+                               void* scratch, cudaStream_t st);
+// ---- Stitchtools::Gather (CPU/StitchTool.cpp:52-96); gmap = rows*cols bytes of device scratch ---------------------------
+void launch_stitch_gather(const uint8_t* L, size_t strideL, const uint8_t* R, size_t strideR, const uint8_t* merged, size_t strideG,
+                          const uint8_t* map, size_t strideM, int rows, int cols, uint8_t* gmap, uint8_t* out, size_t strideO,
+                          cudaStream_t st);
+
 // ---- exhaustive self-test of the branch-free exact division / square root (pf_selftest.cu) ---------------
 int selftest_exact_math(int wmin, int wmax, unsigned long long* out_mismatch_sqrt, unsigned long long* out_mismatch_eps,
                         unsigned long long* out_mismatch_w, int* out_first_bad_w);

@@ -2,8 +2,10 @@
 // and the 8-direction blend-weight search of Stitchtools::prepare / GenerateBlend / countblend
 // (CPU/StitchTool.cpp:7-50, :98-131, :148-191; the reference's own CUDA twin: countblend_Kernel,
 // GPU/StitchTool_GPU.cu:10-66 -- which uses the literal 1.4142 where the CPU path uses sqrt(2); this follows the CPU path).
-// The block-wise in-place blur that follows in GenerateBlend (:133-145) is order-dependent OpenCV ROI filtering and is
-// NOT part of this unit.
+// Second half of the file: the blend smoothing of GenerateBlend (:133-145) -- the order-dependent block-wise cv::blur on
+// ROIs of the image being modified, as a dependency-driven wavefront over blocks, and the final whole-image cv::blur --
+// and Stitchtools::Gather (:52-96).  The box filters follow OpenCV's arithmetic operation by operation (double running
+// sums in the order of RowSum<float,double> / ColumnSum<double,float>); tests/test_stitch_smooth_gather_cpu.py pins that order against cv2.blur.
 #include "pf_kernels.cuh"
 #include "pf_math.cuh"
 
@@ -81,6 +83,282 @@ void launch_stitch_blend_raw(const uint8_t* map, size_t strideM, int rows, int c
     const int step = (cols <= rows) ? cols / 200 : rows / 200;
     dim3 b(32, 8), g((cols + 31) / 32, (rows + 7) / 8);
     k_stitch_blend_raw<<<g, b, 0, st>>>(map, strideM, rows, cols, cols / 5, step, blend, strideB, mdis, strideD);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GenerateBlend smoothing, part 1 (:133-142): for every step x step block in raster order whose MergedDis(y,x) > step,
+// blur(blockROI, blockROI, Size(k,k)).  A block reads a (step+k-1)^2 window of the CURRENT image, so it must run after
+// every earlier block (raster order) within `reach` blocks of it and before every later one: one CTA per block row
+// (persistent, row tickets handed out in order -> the row a CTA waits on is always running or done), blocks of a row left
+// to right, and before a flagged block the CTA waits until each of the `ry` rows above has completed its blocks up to
+// bx + rx.  progress[row] = number of leading blocks of that row that are complete (unflagged blocks count as complete).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101_dev(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+__device__ __forceinline__ int ld_volatile_global_s32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_global_s32(int* p, int v) {
+    asm volatile("st.volatile.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// OpenCV's RowSum<float,double> over one window row S[0 .. n+k-2] -> D[0 .. n-1] (stride ds)
+__device__ __forceinline__ void box_row_sums(const float* S, int n, int k, double* D, int ds) {
+    if (k <= 5) {
+        for (int i = 0; i < n; ++i) {
+            double s = (double)S[i];
+            for (int j = 1; j < k; ++j) s = __dadd_rn(s, (double)S[i + j]);
+            D[i * ds] = s;
+        }
+    } else {
+        double s = 0.0;
+        for (int i = 0; i < k; ++i) s = __dadd_rn(s, (double)S[i]);
+        D[0] = s;
+        for (int i = 0; i + 1 < n; ++i) {
+            s = __dadd_rn(s, __dsub_rn((double)S[i + k], (double)S[i]));
+            D[(i + 1) * ds] = s;
+        }
+    }
+}
+
+struct BlockBlurArgs {
+    float* blend; size_t stride;              // bytes
+    const float* mdis; size_t strideD;        // bytes
+    int rows, cols, step, k, nbx, nby, rx, ry;
+    int* progress;                            // nby ints, zeroed
+    int* ticket;                              // 1 int, zeroed
+};
+
+__global__ void __launch_bounds__(128)
+k_stitch_block_blur(BlockBlurArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nr = a.step + a.k - 1, an = a.k / 2;
+    double* rs = reinterpret_cast<double*>(smem_raw);                     // nr x step
+    float* win = reinterpret_cast<float*>(rs + (size_t)nr * a.step);      // nr x nr
+    unsigned char* flag = reinterpret_cast<unsigned char*>(win + (size_t)nr * nr);   // nbx
+    __shared__ int s_by;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double scale = 1.0 / (double)(a.k * a.k);
+    const float fstep = (float)a.step;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_by = atomicAdd(a.ticket, 1);
+        __syncthreads();
+        const int by = s_by;
+        if (by >= a.nby) break;
+        const int y = by * a.step;
+        const float* mrow = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.mdis) + (size_t)y * a.strideD);
+        for (int bx = tid; bx < a.nbx; bx += nt) flag[bx] = mrow[bx * a.step] > fstep ? 1 : 0;
+        __syncthreads();
+        int bx = 0;
+        while (bx < a.nbx && !flag[bx]) ++bx;
+        if (tid == 0) st_volatile_global_s32(a.progress + by, bx);         // leading unflagged blocks are complete
+        while (bx < a.nbx) {
+            // ---- wait for the rows above ----
+            const int need = min(bx + a.rx + 1, a.nbx);
+            for (int j = tid; j < a.ry; j += nt)
+                if (by - 1 - j >= 0)
+                    while (ld_volatile_global_s32(a.progress + by - 1 - j) < need) __nanosleep(64);
+            __threadfence();
+            __syncthreads();
+            // ---- window of the current image ----
+            const int x = bx * a.step;
+            for (int idx = tid; idx < nr * nr; idx += nt) {
+                const int wy = idx / nr, wx = idx - wy * nr;
+                const int gy = reflect101_dev(y - an + wy, a.rows), gx = reflect101_dev(x - an + wx, a.cols);
+                win[idx] = __ldcg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.blend) + (size_t)gy * a.stride) + gx);
+            }
+            __syncthreads();
+            for (int r = tid; r < nr; r += nt) box_row_sums(win + r * nr, a.step, a.k, rs + (size_t)r * a.step, 1);
+            __syncthreads();
+            for (int i = tid; i < a.step; i += nt) {
+                double SUM = 0.0;
+                for (int r = 0; r < a.k - 1; ++r) SUM = __dadd_rn(SUM, rs[r * a.step + i]);
+                for (int yy = 0; yy < a.step; ++yy) {
+                    const double s0 = __dadd_rn(SUM, rs[(yy + a.k - 1) * a.step + i]);
+                    float* o = reinterpret_cast<float*>(reinterpret_cast<char*>(a.blend) + (size_t)(y + yy) * a.stride) + x + i;
+                    __stcg(o, __double2float_rn(__dmul_rn(s0, scale)));
+                    SUM = __dsub_rn(s0, rs[yy * a.step + i]);
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            ++bx;
+            while (bx < a.nbx && !flag[bx]) ++bx;
+            if (tid == 0) st_volatile_global_s32(a.progress + by, bx);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cv::blur on a whole fp32 image (GenerateBlend :143): row sums in double (one lane per row, 32 rows per warp, tiles
+// staged through shared memory so that global loads and stores stay coalesced), then the column pass (one thread per
+// column, running sum down the rows).  Both passes are sequential along their axis because OpenCV's running sums are.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BOX_KMAX = 64;
+
+__global__ void __launch_bounds__(32)
+k_box_rows(const float* __restrict__ src, size_t stride, int rows, int cols, int k, double* __restrict__ rs) {
+    __shared__ float tile[32][32 + BOX_KMAX + 1];       // extended columns [c0-1, c0+31+k) of 32 rows
+    __shared__ double outt[32][33];
+    const int lane = threadIdx.x, r0 = blockIdx.x * 32, an = k / 2;
+    const int n = 32 + k;
+    double s = 0.0;
+    for (int c0 = 0; c0 < cols; c0 += 32) {
+        for (int rr = 0; rr < 32; ++rr) {
+            const int row = min(r0 + rr, rows - 1);
+            const float* p = reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + (size_t)row * stride);
+            for (int cc = lane; cc < n; cc += 32) tile[rr][cc] = p[reflect101_dev(c0 - 1 - an + cc, cols)];
+        }
+        __syncwarp();
+        const float* S = &tile[lane][1];                 // S[i] = extended column c0 + i
+        if (k <= 5) {
+            for (int i = 0; i < 32; ++i) {
+                double t = (double)S[i];
+                for (int j = 1; j < k; ++j) t = __dadd_rn(t, (double)S[i + j]);
+                outt[lane][i] = t;
+            }
+        } else {
+            for (int i = 0; i < 32; ++i) {
+                if (c0 + i == 0) {
+                    s = 0.0;
+                    for (int j = 0; j < k; ++j) s = __dadd_rn(s, (double)S[j]);
+                } else {
+                    s = __dadd_rn(s, __dsub_rn((double)S[i - 1 + k], (double)S[i - 1]));
+                }
+                outt[lane][i] = s;
+            }
+        }
+        __syncwarp();
+        for (int rr = 0; rr < 32; ++rr)
+            if (r0 + rr < rows && c0 + lane < cols) rs[(size_t)(r0 + rr) * cols + c0 + lane] = outt[rr][lane];
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_box_cols(const double* __restrict__ rs, int rows, int cols, int k, float* __restrict__ dst, size_t stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cols) return;
+    const int an = k / 2;
+    const double scale = 1.0 / (double)(k * k);
+    double SUM = 0.0;
+    for (int r = 0; r < k - 1; ++r) SUM = __dadd_rn(SUM, rs[(size_t)reflect101_dev(r - an, rows) * cols + i]);
+#pragma unroll 4
+    for (int y = 0; y < rows; ++y) {
+        const double sp = rs[(size_t)reflect101_dev(y + k - 1 - an, rows) * cols + i];
+        const double sm = rs[(size_t)reflect101_dev(y - an, rows) * cols + i];
+        const double s0 = __dadd_rn(SUM, sp);
+        reinterpret_cast<float*>(reinterpret_cast<char*>(dst) + (size_t)y * stride)[i] = __double2float_rn(__dmul_rn(s0, scale));
+        SUM = __dsub_rn(s0, sm);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stitchtools::Gather (:52-96)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stitch_gather_map(const uint8_t* __restrict__ map, size_t strideM, const uint8_t* __restrict__ merged, size_t strideG,
+                    int rows, int cols, uint8_t* __restrict__ gmap) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const int v = map[(size_t)y * strideM + x] + (merged[(size_t)y * strideG + (size_t)x * 4 + 3] > 0 ? 75 : 0);
+    gmap[(size_t)y * cols + x] = (uint8_t)min(v, 255);
+}
+
+__global__ void __launch_bounds__(256)
+k_stitch_gather(const uint8_t* __restrict__ L, size_t strideL, const uint8_t* __restrict__ R, size_t strideR,
+                const uint8_t* __restrict__ merged, size_t strideG, const uint8_t* __restrict__ gmap, int rows, int cols,
+                uint8_t* __restrict__ out, size_t strideO) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const long long n = (long long)rows * cols;
+    const int m = gmap[(size_t)y * cols + x];
+    const uchar4 l = *reinterpret_cast<const uchar4*>(L + (size_t)y * strideL + (size_t)x * 4);
+    const uchar4 r = *reinterpret_cast<const uchar4*>(R + (size_t)y * strideR + (size_t)x * 4);
+    uchar4 o = make_uchar4(0, 0, 0, 0);
+    if (m == 100) o = l;
+    else if (m == 50) o = r;
+    else if (m == 225 || m == 125 || m == 175) o = *reinterpret_cast<const uchar4*>(merged + (size_t)y * strideG + (size_t)x * 4);
+    else if (m == 150) {
+        // the reference's unchecked map.at<uchar>(y +- i, x +- i): flat index into the continuous rows x cols map
+        auto GM = [&](int yy, int xx) -> int {
+            const long long p = (long long)yy * cols + xx;
+            return (p >= 0 && p < n) ? (int)gmap[p] : 0;
+        };
+        for (int i = 1; i < 100; ++i) {
+            const int s0 = GM(y, x + i), s1 = GM(y, x - i), s2 = GM(y + i, x), s3 = GM(y - i, x);
+            const int s4 = GM(y - i, x - i), s5 = GM(y - i, x + i), s6 = GM(y + i, x - i), s7 = GM(y + i, x + i);
+            const bool h100 = s0 == 100 || s1 == 100 || s2 == 100 || s3 == 100 || s4 == 100 || s5 == 100 || s6 == 100 || s7 == 100;
+            const bool h50 = s0 == 50 || s1 == 50 || s2 == 50 || s3 == 50 || s4 == 50 || s5 == 50 || s6 == 50 || s7 == 50;
+            if (h100) { o = l; break; }
+            else if (h50) { o = r; break; }
+            else o = make_uchar4(0, 0, 0, 255);
+        }
+    }
+    *reinterpret_cast<uchar4*>(out + (size_t)y * strideO + (size_t)x * 4) = o;
+}
+
+int stitch_smooth_geometry(int rows, int cols, int* step, int* k1, int* k2, size_t* smem_bytes) {
+    const int st = (cols <= rows) ? cols / 200 : rows / 200;
+    *step = st; *k1 = rows / 130; *k2 = rows / 400;
+    if (st < 1 || *k2 < 1) return 1;                    // the reference cannot run either (endless loop / empty kernel)
+    if (*k2 > BOX_KMAX) return 2;
+    const int nr = st + *k1 - 1, nbx = (cols - 1) / st;
+    *smem_bytes = (size_t)nr * st * sizeof(double) + (size_t)nr * nr * sizeof(float) + (size_t)nbx + 16;
+    return *smem_bytes > (size_t)200 * 1024 ? 2 : 0;
+}
+
+size_t stitch_smooth_scratch_bytes(int rows, int cols) {
+    int step, k1, k2; size_t sm;
+    if (stitch_smooth_geometry(rows, cols, &step, &k1, &k2, &sm) != 0) return 0;
+    const int nby = (rows - 1) / step;
+    return (size_t)rows * cols * sizeof(double) + ((size_t)nby + 64) * sizeof(int);
+}
+
+// scratch: stitch_smooth_scratch_bytes(rows, cols) bytes of device memory.  Returns the number of kernels launched (0 on error).
+int launch_stitch_blend_smooth(float* blend, size_t strideB, const float* mdis, size_t strideD, int rows, int cols,
+                               void* scratch, cudaStream_t st) {
+    int step, k1, k2; size_t smem;
+    if (stitch_smooth_geometry(rows, cols, &step, &k1, &k2, &smem) != 0) return 0;
+    BlockBlurArgs a;
+    a.blend = blend; a.stride = strideB; a.mdis = mdis; a.strideD = strideD;
+    a.rows = rows; a.cols = cols; a.step = step; a.k = k1;
+    a.nbx = (cols - 1) / step; a.nby = (rows - 1) / step;
+    const int an = k1 / 2;
+    a.rx = (an + step - 1) / step; a.ry = a.rx;
+    double* rs = reinterpret_cast<double*>(scratch);
+    int* sync = reinterpret_cast<int*>(rs + (size_t)rows * cols);
+    a.progress = sync + 16; a.ticket = sync;
+    cudaMemsetAsync(sync, 0, ((size_t)a.nby + 64) * sizeof(int), st);
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        cudaFuncSetAttribute(k_stitch_block_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done[dev] = true;
+    }
+    const int ncta = a.nby < 592 ? a.nby : 592;
+    if (a.nby > 0 && a.nbx > 0) k_stitch_block_blur<<<ncta, 128, smem, st>>>(a);
+    k_box_rows<<<(rows + 31) / 32, 32, 0, st>>>(blend, strideB, rows, cols, k2, rs);
+    k_box_cols<<<(cols + 127) / 128, 128, 0, st>>>(rs, rows, cols, k2, blend, strideB);
+    return 3;
+}
+
+// gmap: rows*cols bytes of device scratch
+void launch_stitch_gather(const uint8_t* L, size_t strideL, const uint8_t* R, size_t strideR, const uint8_t* merged, size_t strideG,
+                          const uint8_t* map, size_t strideM, int rows, int cols, uint8_t* gmap, uint8_t* out, size_t strideO,
+                          cudaStream_t st) {
+    dim3 b(32, 8), g((cols + 31) / 32, (rows + 7) / 8);
+    k_stitch_gather_map<<<g, b, 0, st>>>(map, strideM, merged, strideG, rows, cols, gmap);
+    k_stitch_gather<<<g, b, 0, st>>>(L, strideL, R, strideR, merged, strideG, gmap, rows, cols, out, strideO);
 }
 
 }  // namespace pf
