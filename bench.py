@@ -274,6 +274,23 @@ def run_b200(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    # ---- the whole stitching iteration around the path (CPU/main.cpp:72-95: Stitchtools::prepare -> flow -> blend -> Gather)
+    # on one canvas of the workload's size, device-resident; reported next to the headline, not part of it ----
+    stitch = None
+    if world == 1 and not args.no_stitch:
+        x = torch.arange(cols, device="cuda")[None, :, None]
+        cL, cR = dL[0].clone(), dR[0].clone()
+        cL[..., 3:4] = torch.where(x < int(0.7 * cols), 255, 0).to(torch.uint8).expand(rows, cols, 1)
+        cR[..., 3:4] = torch.where(x > int(0.3 * cols), 255, 0).to(torch.uint8).expand(rows, cols, 1)
+        cL *= (cL[..., 3:4] > 0)
+        cR *= (cR[..., 3:4] > 0)
+        final = torch.empty_like(cL)
+        step_st = lambda: pf.stitch_iteration(eng, cL, cR, out=final)
+        step_st()
+        st_ms, st_launches = timed(step_st, 2)
+        stitch = {"canvas": "%d x %d, overlap 40 %% of the columns" % (rows, cols), "ms_per_iteration": st_ms / 2,
+                  "mpix_s": rows * cols / 1e6 / (st_ms / 2 / 1e3), "kernel_launches": int(st_launches // 2)}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import orc
@@ -293,7 +310,7 @@ def run_b200(args, rank, world, local_rank):
                    "single_pair_mpix_s": rows * cols / 1e6 / (one_ms / 1e3), "sweep_lanes_per_row": int(os.environ.get("PF_SWEEP_LANES", "2")),
                    "parallelism": "replicas x%d (pairs are independent; NCCL broadcast of the base pair at set-up only)" % world,
                    "l2": "working set ~0.7 GB per pair >> 126 MB L2, no flush needed", "timing": "CUDA events (pf_timer_*), barrier+sync both sides, max over ranks",
-                   "e2e_outputs_match_device_run": bool(same)},
+                   "e2e_outputs_match_device_run": bool(same), "stitch_iteration": stitch},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * 2 * rows * cols * 4,
                 "d2h_bytes_per_step": world * B * 2 * rows * cols * 8, "ms_per_step": e2e_ms / args.steps},
@@ -318,6 +335,7 @@ def main():
     ap.add_argument("--ref-scale", type=int, default=2, help="CPU arm: linear down-scale of the sample pairs")
     ap.add_argument("--cpu-threads", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stitch", action="store_true", help="skip the stitching-iteration measurement (config.stitch_iteration)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

@@ -142,6 +142,13 @@ PF_API int pf_stitch_iteration(pf_engine* engine,
                                void* merged_middle, size_t stride_merged,
                                void* map_u8, size_t stride_map);
 
+/* Replaces the input preparation of the 4-input driver, CPU_4Input/main.cpp:64-79: a column of input k is blanked when
+ * that input's alpha on the canvas' middle row (rows/2) is 0 in that column; colorImageL = image1 + image3 and
+ * colorImageR = image2 + image4 with cv::Mat's saturating 8-bit addition.  images: 4 pointers (1.tif .. 4.tif order), one
+ * common stride.  The two outputs feed pf_stitch_iteration (the rest of that driver is the same single pass). */
+PF_API int pf_four_input_frontend(pf_engine* engine, const void* const images[4], size_t stride_in, int rows, int cols,
+                                  void* image_l, size_t stride_l, void* image_r, size_t stride_r);
+
 /* Pinned host memory for zero-staging transfers (optional; any host pointer is accepted by the calls above). */
 PF_API int pf_host_alloc(void** ptr, size_t bytes);
 PF_API int pf_host_free(void* ptr);

@@ -5,6 +5,7 @@
 //   optical_flow::makeOpticalFlowByName                        CPU/PixFlow.hpp:459-500
 //   optical_flow::NovelViewUtil::combineNovelViews             CPU/OpticalFlow.hpp:19-32, CPU/OpticalFlow.cpp:30-92
 //   optical_flow::NovelViewGenerator(AsymmetricFlow)           CPU/OpticalFlow.hpp:34-70, CPU/OpticalFlow.cpp:94-145
+//   stitch_tools::Stitchtools                                  CPU/StitchTool.hpp:21-61, CPU/StitchTool.cpp:7-191
 //
 // Matrix type: when OpenCV's headers are available (they are not in the build image) cv::Mat is used directly
 // and this header is a drop-in for the reference's PixFlow.hpp + OpticalFlow.hpp.  Otherwise a minimal ref-counted
@@ -45,7 +46,7 @@ struct VrCamException : public std::exception {
 
 namespace pf {
 
-enum { PF_8UC4 = 24, PF_32FC1 = 5, PF_32FC2 = 13 };   // same numeric values as CV_8UC4 / CV_32FC1 / CV_32FC2
+enum { PF_8UC1 = 0, PF_8UC4 = 24, PF_32FC1 = 5, PF_32FC2 = 13 };   // same numeric values as CV_8UC1 / CV_8UC4 / CV_32FC1 / CV_32FC2
 
 #ifdef PIXFLOW_B200_HAVE_OPENCV
 using Mat = cv::Mat;
@@ -72,7 +73,7 @@ public:
     }
     int type() const { return type_; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    size_t elemSize() const { return type_ == PF_8UC4 ? 4 : (type_ == PF_32FC2 ? 8 : 4); }
+    size_t elemSize() const { return type_ == PF_8UC1 ? 1 : (type_ == PF_32FC2 ? 8 : 4); }
     Mat clone() const {
         Mat m;
         if (empty()) return m;
@@ -194,5 +195,74 @@ private:
 };
 
 }  // namespace optical_flow
+
+namespace stitch_tools {
+
+using pf::Mat;
+
+// CPU/StitchTool.hpp:21-61.  Same public members and methods as the reference class; prepare() and Gather() run on the B200
+// (pf_stitch_prepare / pf_stitch_gather).  MatchImages / GenerateBlend / countblend are not separately callable: prepare()
+// is their only caller in the reference (CPU/StitchTool.cpp:15, :35) and runs all three in one device pass.
+class Stitchtools {
+public:
+    Mat ImageL, ImageR;
+    Mat Blend;
+    Mat OverlappedL, OverlappedR;
+    Mat Mergedmiddle;
+    Mat Map;
+    Mat FinalResult;
+    Mat MergedDis;
+
+    Stitchtools() {}
+    ~Stitchtools() {}
+
+    void prepare(const Mat& colorImageL, const Mat& colorImageR) {
+        ImageL = colorImageL.clone();
+        ImageR = colorImageR.clone();
+        const int rows = ImageL.rows, cols = ImageL.cols;
+        Map = pf::make_mat(rows, cols, pf::PF_8UC1);
+        OverlappedL = pf::make_mat(rows, cols, pf::PF_8UC4);
+        OverlappedR = pf::make_mat(rows, cols, pf::PF_8UC4);
+        MergedDis = pf::make_mat(rows, cols, pf::PF_32FC1);
+        Blend = pf::make_mat(rows, cols, pf::PF_32FC1);
+        pf::check(pf_stitch_prepare(engine(), ImageL.data, ImageL.step, ImageR.data, ImageR.step, rows, cols, Map.data, Map.step,
+                                    OverlappedL.data, OverlappedL.step, OverlappedR.data, OverlappedR.step, nullptr, 0,
+                                    MergedDis.data, MergedDis.step, Blend.data, Blend.step));
+    }
+
+    void Gather() {
+        FinalResult = pf::make_mat(ImageL.rows, ImageL.cols, pf::PF_8UC4);
+        pf::check(pf_stitch_gather(engine(), ImageL.data, ImageL.step, ImageR.data, ImageR.step, Mergedmiddle.data, Mergedmiddle.step,
+                                   Map.data, Map.step, ImageL.rows, ImageL.cols, FinalResult.data, FinalResult.step));
+    }
+
+    Mat getImageL() { return ImageL; }
+    Mat getImageR() { return ImageR; }
+    Mat getBlend() { return Blend; }
+    Mat getMap() { return Map; }
+    Mat getOverlappedL() { return OverlappedL; }
+    Mat getOverlappedR() { return OverlappedR; }
+    Mat getFinalResult() { return FinalResult; }
+
+    void setMergedmiddle(const Mat& image) { Mergedmiddle = image.clone(); }
+
+private:
+    pf_engine* engine() {
+        if (!alg_) alg_.reset(new optical_flow::PixFlowB200("pixflow_low"));
+        return alg_->handle();
+    }
+    std::shared_ptr<optical_flow::PixFlowB200> alg_;
+};
+
+// The loop body of the reference driver (CPU/main.cpp:72-95) as one device-resident call; colorImageR / FinalResult may
+// wrap device memory (Mat(rows, cols, type, devptr, step)) to keep the canvas on the GPU across the five iterations.
+inline void stitchIteration(optical_flow::PixFlowB200& flowAlg, const Mat& colorImageL, const Mat& colorImageR, Mat& FinalResult) {
+    if (FinalResult.empty()) FinalResult = pf::make_mat(colorImageL.rows, colorImageL.cols, pf::PF_8UC4);
+    pf::check(pf_stitch_iteration(flowAlg.handle(), colorImageL.data, colorImageL.step, colorImageR.data, colorImageR.step,
+                                  colorImageL.rows, colorImageL.cols, FinalResult.data, FinalResult.step, nullptr, 0, nullptr, 0,
+                                  nullptr, 0));
+}
+
+}  // namespace stitch_tools
 
 #endif  // PIXFLOW_B200_HPP

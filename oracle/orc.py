@@ -308,3 +308,14 @@ def stitch_iteration(imageL, imageR, max_percentage=20):
     final = stitch_gather(imageL, imageR, merged, m)
     return final, dict(map=m, overlappedL=oL, overlappedR=oR, blend_raw=braw, merged_dis=md, blend=blend,
                        flowLtoR=fLR, flowRtoL=fRL, merged=merged)
+
+
+def four_input_frontend(img1, img2, img3, img4):
+    """CPU_4Input/main.cpp:64-79 -> (colorImageL, colorImageR)"""
+    arrs = [_u(a)[0] for a in (img1, img2, img3, img4)]
+    rows, cols, _ = arrs[0].shape
+    ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])
+    L = np.empty((rows, cols, 4), np.uint8)
+    R = np.empty((rows, cols, 4), np.uint8)
+    lib().orc_four_input_frontend(ptrs, rows, cols, L.ctypes.data_as(C.c_void_p), R.ctypes.data_as(C.c_void_p))
+    return L, R

@@ -957,3 +957,21 @@ ORC_API void orc_stitch_gather(const uint8_t* L, const uint8_t* R, const uint8_t
 #undef GM
     free(map);
 }
+
+/* Input preparation of the 4-input driver (CPU_4Input/main.cpp:64-79): blank every column of input k whose alpha on the
+ * middle row is 0, then L = img1 + img3, R = img2 + img4 (cv::Mat operator+ on CV_8UC4 saturates). */
+ORC_API void orc_four_input_frontend(const uint8_t* const img[4], int rows, int cols, uint8_t* L, uint8_t* R) {
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            uint8_t v[4][4];
+            for (int k = 0; k < 4; ++k) {
+                const int keep = img[k][((size_t)(rows / 2) * cols + x) * 4 + 3] != 0;
+                for (int c = 0; c < 4; ++c) v[k][c] = keep ? img[k][((size_t)y * cols + x) * 4 + c] : 0;
+            }
+            for (int c = 0; c < 4; ++c) {
+                const int l = v[0][c] + v[2][c], r = v[1][c] + v[3][c];
+                L[((size_t)y * cols + x) * 4 + c] = (uint8_t)(l > 255 ? 255 : l);
+                R[((size_t)y * cols + x) * 4 + c] = (uint8_t)(r > 255 ? 255 : r);
+            }
+        }
+}

@@ -25,6 +25,7 @@ SIGNATURES = {
     "pf_novel_view": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz]),
     "pf_stitch_prepare": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "pf_stitch_gather": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
+    "pf_four_input_frontend": (_i, [_vp, C.POINTER(_vp), _sz, _i, _i, _vp, _sz, _vp, _sz]),
     "pf_stitch_iteration": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "pf_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "pf_host_free": (_i, [_vp]),

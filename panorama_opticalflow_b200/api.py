@@ -356,6 +356,20 @@ def stitch_iteration(flowAlg, colorImageL, colorImageR, out=None, want_intermedi
     return (out, extra) if want_intermediates else out
 
 
+def four_input_frontend(flowAlg, colorImage1, colorImage2, colorImage3, colorImage4):
+    """The input preparation of the 4-input driver (CPU_4Input/main.cpp:64-79) -> (colorImageL, colorImageR)."""
+    views = [_view(a, np.uint8, 4, "colorImage%d" % (k + 1)) for k, a in enumerate((colorImage1, colorImage2, colorImage3, colorImage4))]
+    rows, cols = views[0][3], views[0][4]
+    if any((v[3], v[4]) != (rows, cols) for v in views) or any(v[2] != views[0][2] for v in views):
+        raise ValueError("the four inputs must have the same size and row stride")
+    ptrs = (C.c_void_p * 4)(*[v[1] for v in views])
+    L = np.empty((rows, cols, 4), np.uint8)
+    R = np.empty((rows, cols, 4), np.uint8)
+    _lib.check(flowAlg._lib.pf_four_input_frontend(flowAlg._h, ptrs, views[0][2], rows, cols, C.c_void_p(L.ctypes.data), cols * 4,
+                                                   C.c_void_p(R.ctypes.data), cols * 4))
+    return L, R
+
+
 def _blend_smooth_for_tests(flowAlg, blend_raw, merged_dis):
     """The smoothing of GenerateBlend (CPU/StitchTool.cpp:133-145) alone, on caller-supplied values (diagnostic entry point
     pf_stage_blend_smooth; used by the parity tests to drive the box filters with adversarial data)."""

@@ -876,6 +876,36 @@ int pf_stitch_gather(pf_engine* e, const void* L, size_t sl, const void* R, size
     return PF_OK;
 }
 
+int pf_four_input_frontend(pf_engine* e, const void* const images[4], size_t stride_in, int rows, int cols,
+                           void* outL, size_t sl, void* outR, size_t sr) {
+    if (!e || !images) return fail(PF_ERR_INVALID_ARGUMENT, "engine or images is NULL");
+    int rc;
+    for (int k = 0; k < 4; ++k)
+        if ((rc = check_image_args(images[k], stride_in, rows, cols, 4, "colorImage1..4")) != PF_OK) return rc;
+    if ((rc = check_image_args(outL, sl, rows, cols, 4, "colorImageL")) != PF_OK) return rc;
+    if ((rc = check_image_args(outR, sr, rows, cols, 4, "colorImageR")) != PF_OK) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    StitchBufs& sb = stitch_bufs(e);
+    RC(sb.ensure(rows, cols));
+    cudaStream_t st = sb.st;
+    const size_t c4 = (size_t)cols * 4;
+    // inputs: in place when on the device, else staged into the (otherwise idle) buffers oL, oR, merged, result
+    uint8_t* stage[4] = {sb.oL, sb.oR, sb.merged, sb.result};
+    const uint8_t* p[4]; size_t ps[4];
+    for (int k = 0; k < 4; ++k) RC(stage_u8(images[k], stride_in, rows, c4, stage[k], &p[k], &ps[k], st));
+    const bool dl = is_device_ptr(outL), dr = is_device_ptr(outR);
+    uint8_t* oL = dl ? (uint8_t*)outL : sb.L;
+    uint8_t* oR = dr ? (uint8_t*)outR : sb.R;
+    pf::launch_four_input(p, ps, rows, cols, oL, dl ? sl : c4, oR, dr ? sr : c4, st);
+    LAUNCHED(1);
+    PF_CUDA(cudaGetLastError());
+    if (!dl) RC(copy_out(outL, sl, sb.L, c4, rows, st));
+    if (!dr) RC(copy_out(outR, sr, sb.R, c4, rows, st));
+    PF_CUDA(cudaStreamSynchronize(st));
+    return PF_OK;
+}
+
 int pf_stitch_iteration(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, int rows, int cols,
                         void* out, size_t so, void* blend, size_t sbl, void* merged, size_t smg, void* map, size_t sm) {
     if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");

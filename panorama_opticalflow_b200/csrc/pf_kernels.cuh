@@ -99,6 +99,10 @@ void launch_stitch_gather(const uint8_t* L, size_t strideL, const uint8_t* R, si
                           const uint8_t* map, size_t strideM, int rows, int cols, uint8_t* gmap, uint8_t* out, size_t strideO,
                           cudaStream_t st);
 
+// ---- CPU_4Input front end (CPU_4Input/main.cpp:64-79): column pre-crop by the middle row's alpha + saturating adds -------
+void launch_four_input(const uint8_t* const img[4], const size_t stride[4], int rows, int cols, uint8_t* outL, size_t strideL,
+                       uint8_t* outR, size_t strideR, cudaStream_t st);
+
 // ---- exhaustive self-test of the branch-free exact division / square root (pf_selftest.cu) ---------------
 int selftest_exact_math(int wmin, int wmax, unsigned long long* out_mismatch_sqrt, unsigned long long* out_mismatch_eps,
                         unsigned long long* out_mismatch_w, int* out_first_bad_w);

@@ -306,6 +306,41 @@ k_stitch_gather(const uint8_t* __restrict__ L, size_t strideL, const uint8_t* __
     *reinterpret_cast<uchar4*>(out + (size_t)y * strideO + (size_t)x * 4) = o;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CPU_4Input front end (CPU_4Input/main.cpp:64-79): a column of input k is blanked when that input's alpha on the middle row
+// (rows/2) of the column is 0; colorImageL = image1 + image3, colorImageR = image2 + image4 (saturating u8 adds).
+// ---------------------------------------------------------------------------------------------------------
+struct FourIn { const uint8_t* img[4]; size_t stride[4]; };
+
+__device__ __forceinline__ uchar4 add_sat_u8x4(uchar4 a, uchar4 b) {
+    return make_uchar4((unsigned char)min(a.x + b.x, 255), (unsigned char)min(a.y + b.y, 255),
+                       (unsigned char)min(a.z + b.z, 255), (unsigned char)min(a.w + b.w, 255));
+}
+
+__global__ void __launch_bounds__(256)
+k_four_input(FourIn in, int rows, int cols, uint8_t* __restrict__ outL, size_t strideL, uint8_t* __restrict__ outR, size_t strideR) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    uchar4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint8_t mid_alpha = in.img[k][(size_t)(rows / 2) * in.stride[k] + (size_t)x * 4 + 3];
+        const uchar4 p = *reinterpret_cast<const uchar4*>(in.img[k] + (size_t)y * in.stride[k] + (size_t)x * 4);
+        v[k] = mid_alpha ? p : make_uchar4(0, 0, 0, 0);
+    }
+    *reinterpret_cast<uchar4*>(outL + (size_t)y * strideL + (size_t)x * 4) = add_sat_u8x4(v[0], v[2]);
+    *reinterpret_cast<uchar4*>(outR + (size_t)y * strideR + (size_t)x * 4) = add_sat_u8x4(v[1], v[3]);
+}
+
+void launch_four_input(const uint8_t* const img[4], const size_t stride[4], int rows, int cols, uint8_t* outL, size_t strideL,
+                       uint8_t* outR, size_t strideR, cudaStream_t st) {
+    FourIn in;
+    for (int k = 0; k < 4; ++k) { in.img[k] = img[k]; in.stride[k] = stride[k]; }
+    dim3 b(32, 8), g((cols + 31) / 32, (rows + 7) / 8);
+    k_four_input<<<g, b, 0, st>>>(in, rows, cols, outL, strideL, outR, strideR);
+}
+
 int stitch_smooth_geometry(int rows, int cols, int* step, int* k1, int* k2, size_t* smem_bytes) {
     const int st = (cols <= rows) ? cols / 200 : rows / 200;
     *step = st; *k1 = rows / 130; *k2 = rows / 400;

@@ -177,3 +177,14 @@ def test_stitch_iterations_chained_on_device(engine_search):
     pf.stitch_iteration(engine_search, dev[2], out1, out=out2)
     assert_bit_equal(out2.cpu().numpy(), host, "device-chained vs host-chained")
     assert (host[..., 3] > 0).sum() > (imgs[0][..., 3] > 0).sum()
+
+
+@pytest.mark.gpu
+def test_four_input_frontend_vs_oracle(orc, engine_low):
+    import panorama_opticalflow_b200 as pf
+    from test_stitch_smooth_gather_cpu import _four_inputs
+    imgs = _four_inputs(203, 331, 8)
+    L, R = pf.api.four_input_frontend(engine_low, *imgs)
+    wL, wR = orc.four_input_frontend(*imgs)
+    assert_bit_equal(L, wL, "colorImageL")
+    assert_bit_equal(R, wR, "colorImageR")

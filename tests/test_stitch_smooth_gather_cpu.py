@@ -128,3 +128,25 @@ def test_gather_against_numpy(orc, rows, cols, wrap):
     assert (mp == 150).sum() > 100 and (mp == 75).sum() == min(40, zy.size) > 0
     if cols == 900:
         assert ((got == (0, 0, 0, 255)).all(-1) & (mp == 150)).any(), "no hole further than 99 px from both images"
+
+
+def _four_inputs(rows, cols, seed):
+    rng = np.random.default_rng(seed)
+    imgs = []
+    for k in range(4):
+        a = rng.integers(0, 256, (rows, cols, 4), dtype=np.uint8)
+        x = np.mgrid[0:rows, 0:cols][1]
+        a[..., 3] = np.where((x + 37 * k) % 90 < 55, 255, 0)
+        a[rows // 2, rng.integers(0, cols, 12), 3] = 0     # columns blanked only because of the middle row
+        imgs.append(a)
+    return imgs
+
+
+def test_four_input_frontend_against_numpy(orc):
+    rows, cols = 61, 200
+    imgs = _four_inputs(rows, cols, 4)
+    L, R = orc.four_input_frontend(*imgs)
+    kept = [np.where((a[rows // 2, :, 3] != 0)[None, :, None], a, 0).astype(int) for a in imgs]
+    assert np.array_equal(L, np.minimum(kept[0] + kept[2], 255).astype(np.uint8))
+    assert np.array_equal(R, np.minimum(kept[1] + kept[3], 255).astype(np.uint8))
+    assert (L == 255).any() and (kept[0] + kept[2] > 255).any()
