@@ -145,7 +145,7 @@ struct Workspace {
         sMain = nullptr; evReady = nullptr;
     }
 
-    int init(int rows, int cols, int pad) {
+    int init(int rows, int cols, int pad, int idx = 0) {
         plan.build(rows, cols, pad);
         const Plan& p = plan;
         const size_t px0 = (size_t)p.dw * p.dh;
@@ -163,7 +163,23 @@ struct Workspace {
             PF_CUDA(cudaMalloc(&bnd[k], (p.bnd_lines + 1) * sizeof(uint4)));
             PF_CUDA(cudaMalloc(&tickets[k], (size_t)p.L * 2 * sizeof(int)));
             PF_CUDA(cudaMalloc(&out[k], (size_t)rows * cols * sizeof(float2)));
-            PF_CUDA(cudaStreamCreateWithFlags(&sDir[k], cudaStreamNonBlocking));
+            {
+                // Pairs in flight get DIFFERENT stream priorities (PF_STREAM_PRIO: 0 off, 1 round-robin over the
+                // device's priority levels, 2 contiguous groups of 4; measured on B200: no gain, default off): identical pairs launched together would
+                // otherwise march in lockstep -- all in their throughput-bound stencil kernels at the same time, then all
+                // in their latency-bound sweeps -- and the two kinds of work would never overlap.
+                static int mode = -1, least = 0, greatest = 0;
+                if (mode < 0) {
+                    const char* ev = getenv("PF_STREAM_PRIO");
+                    mode = ev ? atoi(ev) : 0;
+                    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+                }
+                const int nlev = least - greatest + 1;
+                int prio = least;
+                if (mode == 1 && nlev > 1) prio = greatest + idx % nlev;
+                if (mode == 2 && nlev > 1) prio = greatest + (idx / 4) % nlev;
+                PF_CUDA(cudaStreamCreateWithPriority(&sDir[k], cudaStreamNonBlocking, prio));
+            }
             PF_CUDA(cudaEventCreateWithFlags(&evDone[k], cudaEventDisableTiming));
         }
         PF_CUDA(cudaMalloc(&Ipre, px0 * sizeof(float)));
@@ -206,7 +222,7 @@ struct pf_engine {
         if (!w) {
             std::lock_guard<std::mutex> cg(g_capture_mu);
             w = new Workspace();
-            const int rc = w->init(rows, cols, pad);
+            const int rc = w->init(rows, cols, pad, idx);
             if (rc != PF_OK) { delete w; pool[idx] = nullptr; return rc; }
             pool[idx] = w;
         }

@@ -15,6 +15,27 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 
+// ---- Blackwell packed fp32x2 arithmetic (FFMA2 / FADD2, sm_100+) -------------------------------------------------------
+// Two independent IEEE round-to-nearest fp32 operations per instruction: the (x, y) channels of a flow vector or of a
+// gradient pair go through identical arithmetic, so every packed result is bit-identical to the two scalar __f*_rn
+// operations it replaces, at half the issue slots (the FMA pipe is occupied for two cycles; measured on B200 with
+// tools/microbench_f32x2.cu: same 4.5-cycle dependent latency as the scalar forms).
+// ptxas 12.9 contracts mul.f32x2 + add.f32x2 (and __fmul2_rn + __fadd2_rn) into one FFMA2 even under --fmad=false, which
+// would change the rounding; the packed multiply is therefore written as fma(a, b, {-0,-0}) with the -0 pair read from
+// constant memory, opaque to the compiler: RN(a*b + (-0)) == RN(a*b) for every a, b (signed zeros included), and an fma
+// cannot be contracted with a following add.  Checked on 2^24 random bit patterns by the same micro-benchmark.
+typedef unsigned long long f2p;            // {lo = x, hi = y}: the register pair of a float2
+static __constant__ f2p c_pf_negzero2 = 0x8000000080000000ull;
+__device__ __forceinline__ f2p pk(float lo, float hi) { f2p r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2p pk(float2 v) { return pk(v.x, v.y); }
+__device__ __forceinline__ float2 upk(f2p v) { float2 o; asm("mov.b64 {%0,%1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(v)); return o; }
+__device__ __forceinline__ f2p pfma(f2p a, f2p b, f2p c) { f2p r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2p padd(f2p a, f2p b) { f2p r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2p psub(f2p a, f2p b) { f2p r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2p pmul(f2p a, f2p b) { return pfma(a, b, c_pf_negzero2); }
+__device__ __forceinline__ f2p pmuls(f2p a, float s) { return pfma(a, pk(s, s), c_pf_negzero2); }
+__device__ __forceinline__ f2p pneg(f2p a) { return psub(0ull, a); }      // only used where the sign of a zero is irrelevant
+
 __device__ __forceinline__ int clampi(int x, int a, int b) { return x < a ? a : (x > b ? b : x); }
 
 // BORDER_REFLECT_101
@@ -158,6 +179,24 @@ __device__ __forceinline__ float div_by_const(float x, float d, float rd) {
     const float rem = __fmaf_rn(-q, d, x);
     const float r = __fmaf_rn(rem, rd, q);
     return x == 0.0f ? x : r;          // keeps the sign of a zero numerator (d > 0)
+}
+
+// the same two sequences on pairs.  div2_by_const needs both numerators to be >= +0 or non-zero (a -0 numerator would come
+// back as +0; the callers divide |x|-products and differences of errors, never -0).
+__device__ __forceinline__ f2p div2_by_const(f2p x, float d, float rd) {
+    const f2p q = pmuls(x, rd);
+    const f2p rem = pfma(q, pk(-d, -d), x);          // x - q*d, exact (FMA)
+    return pfma(rem, pk(rd, rd), q);
+}
+__device__ __forceinline__ f2p sqrt2_exact_fast(float a0, float a1) {
+    float y0, y1;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(a0));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(a1));
+    const f2p a = pk(a0, a1), y = pk(y0, y1);
+    const f2p g = pmul(a, y), h = pmuls(y, 0.5f);
+    const f2p r = pfma(pneg(g), g, a);
+    const float2 s = upk(pfma(r, h, g));
+    return pk(a0 == 0.0f ? a0 : s.x, a1 == 0.0f ? a1 : s.y);
 }
 
 // sqrt(a) for a in (2^-80, 2^80) or a == 0: rsqrt seed, one Newton step with exact residual

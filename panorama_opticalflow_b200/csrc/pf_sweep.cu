@@ -209,6 +209,36 @@ struct SweepConst {
     float wm2, hm2, fw, rcp_w, rcp_eps;
 };
 
+// The part of errorFunction (CPU/PixFlow.hpp:447-455) after the bilinear gather, with the (x, y) channel pairs on the packed
+// fp32x2 pipe (pf_math.cuh): G1 = (I1x, I1y) at the matched position.  Same operations, same order, same roundings as the
+// scalar form.  accumulate: fold the operand keys into `tiny` (several probes on one lane) instead of overwriting it.
+template <bool SLOW>
+__device__ __forceinline__ float err_tail(const SweepConst& k, f2p G1, float2 g0, float2 bl, float fx, float fy, unsigned& tiny, bool accumulate) {
+    const f2p D = psub(pk(bl), pk(fx, fy));
+    const float2 d2 = upk(pmul(D, D));
+    const float ss = fadd(d2.x, d2.y);
+    const f2p E = psub(pk(g0), G1);
+    const float2 e2 = upk(pmul(E, E));
+    const float gs = fadd(e2.x, e2.y);
+    const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
+    float smooth, grad, ry, rx;
+    if (SLOW) {
+        smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
+        ry = __fdiv_rn(ty, k.fw); rx = __fdiv_rn(tx, k.fw);
+    } else {
+        const float2 sq = upk(sqrt2_exact_fast(ss, gs));
+        smooth = sq.x; grad = sq.y;
+        const float2 rr = upk(div2_by_const(pk(ty, tx), k.fw, k.rcp_w));      // ty, tx >= +0
+        ry = rr.x; rx = rr.y;
+        const unsigned key = min(min(tiny_key(ss), tiny_key(gs)), min(tiny_key(ty), tiny_key(tx)));
+        tiny = accumulate ? min(tiny, key) : key;
+    }
+    float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
+    err = fadd(err, ry);
+    err = fadd(err, rx);
+    return err;
+}
+
 // errorFunction (CPU/PixFlow.hpp:427-456) for ONE flow candidate, gathering I1's gradients from the skewed layout.
 // SLOW = false: branch-free exact sequences; `tiny` collects the keys of their operands (see tiny_key).
 template <int POSX, bool SLOW>
@@ -232,35 +262,10 @@ __device__ __forceinline__ float eval_err(const SweepConst& k, float xf, float y
         pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
         cp_async16(k.touch, k.G1s + pi);
     }
-    float g1x, g1y;
-    {
-        const float a2 = fsub(f10.x, f00.x), a3 = fsub(f01.x, f00.x);
-        const float a4 = fsub(fsub(fadd(f00.x, f11.x), f10.x), f01.x);
-        g1x = fadd(fadd(fadd(f00.x, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
-    }
-    {
-        const float a2 = fsub(f10.y, f00.y), a3 = fsub(f01.y, f00.y);
-        const float a4 = fsub(fsub(fadd(f00.y, f11.y), f10.y), f01.y);
-        g1y = fadd(fadd(fadd(f00.y, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
-    }
-    const float dX = fsub(bl.x, fx), dY = fsub(bl.y, fy);
-    const float ss = fadd(fmul(dX, dX), fmul(dY, dY));
-    const float ex = fsub(g0.x, g1x), ey = fsub(g0.y, g1y);
-    const float gs = fadd(fmul(ex, ex), fmul(ey, ey));
-    const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
-    float smooth, grad, ry, rx;
-    if (SLOW) {
-        smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
-        ry = __fdiv_rn(ty, k.fw); rx = __fdiv_rn(tx, k.fw);
-    } else {
-        smooth = sqrt_exact_fast(ss); grad = sqrt_exact_fast(gs);
-        ry = div_by_const(ty, k.fw, k.rcp_w); rx = div_by_const(tx, k.fw, k.rcp_w);
-        tiny = min(min(tiny_key(ss), tiny_key(gs)), min(tiny_key(ty), tiny_key(tx)));
-    }
-    float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
-    err = fadd(err, ry);
-    err = fadd(err, rx);
-    return err;
+    const f2p F00 = pk(f00), F10 = pk(f10), F01 = pk(f01), F11 = pk(f11);
+    const f2p A2 = psub(F10, F00), A3 = psub(F01, F00), A4 = psub(psub(padd(F00, F11), F10), F01);
+    const f2p G1 = padd(padd(padd(F00, pmuls(A2, xR)), pmuls(A3, yR)), pmuls(pmuls(A4, xR), yR));
+    return err_tail<SLOW>(k, G1, g0, bl, fx, fy, tiny, false);
 }
 
 // The three probes f, f+(eps,0), f+(0,eps) of ONE candidate on one lane (2 or 1 lanes per row).  The probes almost always
@@ -278,53 +283,27 @@ __device__ __forceinline__ SkewCell skew_cell(const SweepConst& k, float mxr, fl
     return c;
 }
 
-struct SkewTaps { float2 f00, f10, f01, f11; };
+// the four texels of a bilinear cell as the coefficients of getPixBilinear32FExtend (:415-424), both planes packed
+struct SkewCoef { f2p f00, a2, a3, a4; };
 
 template <int POSX>
-__device__ __forceinline__ SkewTaps skew_gather(const SweepConst& k, int gi) {
+__device__ __forceinline__ SkewCoef skew_gather(const SweepConst& k, int gi) {
     const float2* p00 = k.G1s + gi;
     const float2* p1 = p00 + k.pitch;            // anti-diagonal +1: (x0,y0+1) and (x0+1,y0) are adjacent
     const float2* p2 = p1 + k.pitch;             // anti-diagonal +2
-    SkewTaps t;
-    t.f00 = __ldg(p00);
-    t.f10 = __ldg(p1 + (POSX ? 1 : 0));
-    t.f01 = __ldg(p1 + (POSX ? 0 : 1));
-    t.f11 = __ldg(p2 + 1);
-    return t;
+    const f2p F00 = pk(__ldg(p00)), F10 = pk(__ldg(p1 + (POSX ? 1 : 0))), F01 = pk(__ldg(p1 + (POSX ? 0 : 1))), F11 = pk(__ldg(p2 + 1));
+    SkewCoef c;
+    c.f00 = F00;
+    c.a2 = psub(F10, F00); c.a3 = psub(F01, F00);
+    c.a4 = psub(psub(padd(F00, F11), F10), F01);
+    return c;
 }
 
 template <bool SLOW>
-__device__ __forceinline__ float err_from_taps(const SweepConst& k, const SkewTaps& t, float xR, float yR, float2 g0, float2 bl,
+__device__ __forceinline__ float err_from_taps(const SweepConst& k, const SkewCoef& t, float xR, float yR, float2 g0, float2 bl,
                                                float fx, float fy, unsigned& tiny) {
-    float g1x, g1y;
-    {
-        const float a2 = fsub(t.f10.x, t.f00.x), a3 = fsub(t.f01.x, t.f00.x);
-        const float a4 = fsub(fsub(fadd(t.f00.x, t.f11.x), t.f10.x), t.f01.x);
-        g1x = fadd(fadd(fadd(t.f00.x, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
-    }
-    {
-        const float a2 = fsub(t.f10.y, t.f00.y), a3 = fsub(t.f01.y, t.f00.y);
-        const float a4 = fsub(fsub(fadd(t.f00.y, t.f11.y), t.f10.y), t.f01.y);
-        g1y = fadd(fadd(fadd(t.f00.y, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
-    }
-    const float dX = fsub(bl.x, fx), dY = fsub(bl.y, fy);
-    const float ss = fadd(fmul(dX, dX), fmul(dY, dY));
-    const float ex = fsub(g0.x, g1x), ey = fsub(g0.y, g1y);
-    const float gs = fadd(fmul(ex, ex), fmul(ey, ey));
-    const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
-    float smooth, grad, ry, rx;
-    if (SLOW) {
-        smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
-        ry = __fdiv_rn(ty, k.fw); rx = __fdiv_rn(tx, k.fw);
-    } else {
-        smooth = sqrt_exact_fast(ss); grad = sqrt_exact_fast(gs);
-        ry = div_by_const(ty, k.fw, k.rcp_w); rx = div_by_const(tx, k.fw, k.rcp_w);
-        tiny = min(tiny, min(min(tiny_key(ss), tiny_key(gs)), min(tiny_key(ty), tiny_key(tx))));
-    }
-    float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
-    err = fadd(err, ry);
-    err = fadd(err, rx);
-    return err;
+    const f2p G1 = padd(padd(padd(t.f00, pmuls(t.a2, xR)), pmuls(t.a3, yR)), pmuls(pmuls(t.a4, xR), yR));
+    return err_tail<SLOW>(k, G1, g0, bl, fx, fy, tiny, true);
 }
 
 template <int POSX, bool SLOW>
@@ -335,13 +314,13 @@ __device__ __forceinline__ void eval_err3(const SweepConst& k, float xf, float y
     const SkewCell c0 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy0));
     const SkewCell c1 = skew_cell<POSX>(k, fadd(xf, fx1), fadd(yf, fy0));
     const SkewCell c2 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy2));
-    const SkewTaps t0 = skew_gather<POSX>(k, c0.gi);
+    const SkewCoef t0 = skew_gather<POSX>(k, c0.gi);
     {   // warm L1 with the anti-diagonal the gather reaches a few steps from now (asynchronous copy into a scratch slot)
         int pi = c0.gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
         pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
         cp_async16(k.touch, k.G1s + pi);
     }
-    SkewTaps t1 = t0, t2 = t0;
+    SkewCoef t1 = t0, t2 = t0;
     if (__any_sync(0xffffffffu, c1.gi != c0.gi || c2.gi != c0.gi)) {     // rare: a probe crossed a texel boundary
         t1 = skew_gather<POSX>(k, c1.gi);
         t2 = skew_gather<POSX>(k, c2.gi);
@@ -351,24 +330,25 @@ __device__ __forceinline__ void eval_err3(const SweepConst& k, float xf, float y
     v[2] = err_from_taps<SLOW>(k, t2, c2.xR, c2.yR, g0, bl, fx0, fy2, tiny);
 }
 
+// One candidate's gradient step (CPU/PixFlow.hpp:321, :364-386) from its three errors {E, E(+dx), E(+dy)}: r = cand - step * dE/eps
+template <bool SLOW>
+__device__ __forceinline__ float2 finish_candidate(const SweepConst& k, const float e3[3], float2 cand, unsigned& tiny) {
+    const float2 d = upk(psub(pk(e3[1], e3[2]), pk(e3[0], e3[0])));
+    f2p Q;
+    if (SLOW) {
+        Q = pk(__fdiv_rn(d.x, PF_GRAD_EPS), __fdiv_rn(d.y, PF_GRAD_EPS));
+    } else {
+        Q = div2_by_const(pk(d.x, d.y), PF_GRAD_EPS, k.rcp_eps);              // a difference of errors is never -0
+        tiny = min(tiny_key(fabsf(d.x)), tiny_key(fabsf(d.y)));
+    }
+    return upk(psub(pk(cand), pmuls(Q, PF_GRAD_STEP)));
+}
+
 // From the six errors {L, L+dx, L+dy, U, U+dx, U+dy} of a pixel to its result: finish both candidates' gradient steps
 // (CPU/PixFlow.hpp:321, :364-386) and select in the reference's order (:318-320: left proposal first, then up, strict <).
-template <bool SLOW>
-__device__ __forceinline__ float2 finish_pixel(const SweepConst& k, const float e6[6], float2 left, float2 up,
-                                               bool leftValid, bool upValid, float4 A, unsigned& tiny) {
-    float eL = e6[0], eU = e6[3];
-    const float dLx = fsub(e6[1], eL), dLy = fsub(e6[2], eL), dUx = fsub(e6[4], eU), dUy = fsub(e6[5], eU);
-    float qLx, qLy, qUx, qUy;
-    if (SLOW) {
-        qLx = __fdiv_rn(dLx, PF_GRAD_EPS); qLy = __fdiv_rn(dLy, PF_GRAD_EPS);
-        qUx = __fdiv_rn(dUx, PF_GRAD_EPS); qUy = __fdiv_rn(dUy, PF_GRAD_EPS);
-    } else {
-        qLx = div_by_const(dLx, PF_GRAD_EPS, k.rcp_eps); qLy = div_by_const(dLy, PF_GRAD_EPS, k.rcp_eps);
-        qUx = div_by_const(dUx, PF_GRAD_EPS, k.rcp_eps); qUy = div_by_const(dUy, PF_GRAD_EPS, k.rcp_eps);
-        tiny = min(min(tiny_key(fabsf(dLx)), tiny_key(fabsf(dLy))), min(tiny_key(fabsf(dUx)), tiny_key(fabsf(dUy))));
-    }
-    const float2 rL = make_float2(fsub(left.x, fmul(PF_GRAD_STEP, qLx)), fsub(left.y, fmul(PF_GRAD_STEP, qLy)));
-    const float2 rU = make_float2(fsub(up.x, fmul(PF_GRAD_STEP, qUx)), fsub(up.y, fmul(PF_GRAD_STEP, qUy)));
+// the reference's two compares (:318-320: left proposal first, then up, strict <) between the pixel's own record A = {E(f0), r0}
+// and the finished candidates
+__device__ __forceinline__ float2 select_result(float eL, float2 rL, float eU, float2 rU, bool leftValid, bool upValid, float4 A) {
     const float POS_INF = __int_as_float(0x7f800000);
     eL = leftValid ? eL : POS_INF;
     eU = upValid ? eU : POS_INF;
@@ -377,6 +357,17 @@ __device__ __forceinline__ float2 finish_pixel(const SweepConst& k, const float 
     if (eL < cur) { out = rL; cur = eL; }
     if (eU < cur) { out = rU; cur = eU; }
     return out;
+}
+
+// From the six errors {L, L+dx, L+dy, U, U+dx, U+dy} of a pixel to its result: finish both candidates' gradient steps, then select.
+template <bool SLOW>
+__device__ __forceinline__ float2 finish_pixel(const SweepConst& k, const float e6[6], float2 left, float2 up,
+                                               bool leftValid, bool upValid, float4 A, unsigned& tiny) {
+    unsigned t1 = 0xffffffffu, t2 = 0xffffffffu;
+    const float2 rL = finish_candidate<SLOW>(k, e6, left, t1);
+    const float2 rU = finish_candidate<SLOW>(k, e6 + 3, up, t2);
+    tiny = min(t1, t2);
+    return select_result(e6[0], rL, e6[3], rU, leftValid, upValid, A);
 }
 
 // Shared memory of one sweep CTA.
@@ -539,24 +530,27 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
                     vmax = fmaxf(vmax, fabsf(v[q]));
                     if (!(v[q] == v[q])) vmax = __int_as_float(0x7f800000);      // NaN -> flagged
                 }
-                // every lane of the row gets the six errors {L, L+dx, L+dy, U, U+dx, U+dy}
-                float e6[6];
-                if (P == 8) {
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) e6[q] = __shfl_sync(full, v[0], gbase + q);
-                } else if (P == 2) {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const float o = __shfl_xor_sync(full, v[q], 1);
-                        e6[q] = sub == 0 ? v[q] : o;
-                        e6[3 + q] = sub == 0 ? o : v[q];
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) e6[q] = v[q % G::NQ];
-                }
                 unsigned t2 = 0xffffffffu;
-                out = finish_pixel<SLOW>(k, e6, res, up, i > 0, j > 0, A, t2);
+                if constexpr (P == 2) {
+                    // each lane finishes ITS candidate's gradient step, then the pair swaps {E, r.x, r.y}
+                    const float2 mine = finish_candidate<SLOW>(k, v, sub != 0 ? up : res, t2);
+                    const float oe = __shfl_xor_sync(full, v[0], 1);
+                    const float ox = __shfl_xor_sync(full, mine.x, 1), oy = __shfl_xor_sync(full, mine.y, 1);
+                    const float2 other = make_float2(ox, oy);
+                    out = select_result(sub == 0 ? v[0] : oe, sub == 0 ? mine : other, sub == 0 ? oe : v[0], sub == 0 ? other : mine,
+                                        i > 0, j > 0, A);
+                } else {
+                    // every lane of the row gets the six errors {L, L+dx, L+dy, U, U+dx, U+dy}
+                    float e6[6];
+                    if (P == 8) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) e6[q] = __shfl_sync(full, v[0], gbase + q);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) e6[q] = v[q % G::NQ];
+                    }
+                    out = finish_pixel<SLOW>(k, e6, res, up, i > 0, j > 0, A, t2);
+                }
                 tkey = min(tkey, t2);
             };
             run(std::false_type());
