@@ -10,7 +10,7 @@ struct PrepArgs {
     const float* alpha0; const float* alpha1;
     const float2* G0; const float2* G1;      // row-major gradients of image 0 (at the pixel) and image 1 (gathered)
     SweepRec* rec;                           // wavefront-packed output
-    int R;                                   // rows per sweep warp
+    int R, logR;                             // rows per sweep warp (4, 16 or 32) and its log2
     int dir;                                 // +1 forward sweep, -1 backward sweep
 };
 
@@ -36,45 +36,45 @@ __device__ __forceinline__ BilCell bil_cell_rm(const ErrCtx& c, float x, float y
     return b;
 }
 
-struct Texels { float2 f00, f10, f01, f11; };
+// the four texels of a bilinear cell as the coefficients of getPixBilinear32FExtend (:415-424), both gradient planes packed
+// (fp32x2, pf_math.cuh)
+struct BilCoef { f2p f00, a2, a3, a4; };
 
-__device__ __forceinline__ Texels load_texels_rm(const ErrCtx& c, int x0, int y0) {
+__device__ __forceinline__ BilCoef load_coef_rm(const ErrCtx& c, int x0, int y0) {
     const float2* p = c.G1 + (size_t)y0 * c.w + x0;
-    Texels t;
-    t.f00 = __ldg(p); t.f10 = __ldg(p + 1); t.f01 = __ldg(p + c.w); t.f11 = __ldg(p + c.w + 1);
+    const f2p F00 = pk(__ldg(p)), F10 = pk(__ldg(p + 1)), F01 = pk(__ldg(p + c.w)), F11 = pk(__ldg(p + c.w + 1));
+    BilCoef t;
+    t.f00 = F00;
+    t.a2 = psub(F10, F00); t.a3 = psub(F01, F00);
+    t.a4 = psub(psub(padd(F00, F11), F10), F01);
     return t;
 }
 
-__device__ __forceinline__ float2 bil_interp(const Texels& t, float xR, float yR) {      // :415-424, both planes
-    float2 r;
-    {
-        const float a2 = fsub(t.f10.x, t.f00.x), a3 = fsub(t.f01.x, t.f00.x);
-        const float a4 = fsub(fsub(fadd(t.f00.x, t.f11.x), t.f10.x), t.f01.x);
-        r.x = fadd(fadd(fadd(t.f00.x, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
-    }
-    {
-        const float a2 = fsub(t.f10.y, t.f00.y), a3 = fsub(t.f01.y, t.f00.y);
-        const float a4 = fsub(fsub(fadd(t.f00.y, t.f11.y), t.f10.y), t.f01.y);
-        r.y = fadd(fadd(fadd(t.f00.y, fmul(a2, xR)), fmul(a3, yR)), fmul(fmul(a4, xR), yR));
-    }
-    return r;
+__device__ __forceinline__ f2p bil_interp(const BilCoef& t, float xR, float yR) {
+    return padd(padd(padd(t.f00, pmuls(t.a2, xR)), pmuls(t.a3, yR)), pmuls(pmuls(t.a4, xR), yR));
 }
 
+// errorFunction after the gather (CPU/PixFlow.hpp:447-455); `tiny` / `vmax` collect what the range check of the branch-free
+// exact sequences needs (see emit_record)
 template <bool SLOW>
-__device__ __forceinline__ float err_from_g1(const ErrCtx& c, float rcp_w, float2 g0, float2 bl, float2 g1, float fx, float fy, bool& bad) {
-    const float dX = fsub(bl.x, fx), dY = fsub(bl.y, fy);
-    const float ss = fadd(fmul(dX, dX), fmul(dY, dY));
-    const float ex = fsub(g0.x, g1.x), ey = fsub(g0.y, g1.y);
-    const float gs = fadd(fmul(ex, ex), fmul(ey, ey));
+__device__ __forceinline__ float err_from_g1(const ErrCtx& c, float rcp_w, float2 g0, float2 bl, f2p g1, float fx, float fy, unsigned& tiny) {
+    const f2p D = psub(pk(bl), pk(fx, fy));
+    const float2 d2 = upk(pmul(D, D));
+    const float ss = fadd(d2.x, d2.y);
+    const f2p E = psub(pk(g0), g1);
+    const float2 e2 = upk(pmul(E, E));
+    const float gs = fadd(e2.x, e2.y);
     const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
     float smooth, grad, ry, rx;
     if (SLOW) {
         smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
         ry = __fdiv_rn(ty, c.fw); rx = __fdiv_rn(tx, c.fw);
     } else {
-        smooth = sqrt_exact_fast(ss); grad = sqrt_exact_fast(gs);
-        ry = div_by_const(ty, c.fw, rcp_w); rx = div_by_const(tx, c.fw, rcp_w);
-        bad = bad || !(in_sqrt_range(ss) && in_sqrt_range(gs) && in_div_range(ty) && in_div_range(tx));
+        const float2 sq = upk(sqrt2_exact_fast(ss, gs));
+        smooth = sq.x; grad = sq.y;
+        const float2 rr = upk(div2_by_const(pk(ty, tx), c.fw, rcp_w));        // ty, tx >= +0
+        ry = rr.x; rx = rr.y;
+        tiny = min(tiny, min(min(tiny_key(ss), tiny_key(gs)), min(tiny_key(ty), tiny_key(tx))));
     }
     float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
     err = fadd(err, ry);
@@ -97,34 +97,38 @@ __device__ __forceinline__ void emit_record(const PrepArgs& a, const ErrCtx& c, 
         const BilCell c0 = bil_cell_rm(c, fadd(xf, f.x), fadd(yf, f.y));
         const BilCell c1 = bil_cell_rm(c, fadd(xf, fx1), fadd(yf, fy1));
         const BilCell c2 = bil_cell_rm(c, fadd(xf, fx2), fadd(yf, fy2));
-        const Texels t0 = load_texels_rm(c, c0.x0, c0.y0);
-        Texels t1 = t0, t2 = t0;
-        if (c1.x0 != c0.x0 || c1.y0 != c0.y0) t1 = load_texels_rm(c, c1.x0, c1.y0);    // probe crossed a cell boundary
-        if (c2.x0 != c0.x0 || c2.y0 != c0.y0) t2 = load_texels_rm(c, c2.x0, c2.y0);
-        const float2 g1a = bil_interp(t0, c0.xR, c0.yR), g1b = bil_interp(t1, c1.xR, c1.yR), g1c = bil_interp(t2, c2.xR, c2.yR);
+        const BilCoef t0 = load_coef_rm(c, c0.x0, c0.y0);
+        BilCoef t1 = t0, t2 = t0;
+        if (c1.x0 != c0.x0 || c1.y0 != c0.y0) t1 = load_coef_rm(c, c1.x0, c1.y0);    // probe crossed a cell boundary
+        if (c2.x0 != c0.x0 || c2.y0 != c0.y0) t2 = load_coef_rm(c, c2.x0, c2.y0);
+        const f2p g1a = bil_interp(t0, c0.xR, c0.yR), g1b = bil_interp(t1, c1.xR, c1.yR), g1c = bil_interp(t2, c2.xR, c2.yR);
         const float rcp_w = __frcp_rn(c.fw), rcp_eps = __frcp_rn(PF_GRAD_EPS);
-        bool bad = false;
-        float e0 = err_from_g1<false>(c, rcp_w, g0, bl, g1a, f.x, f.y, bad);
-        float ex = err_from_g1<false>(c, rcp_w, g0, bl, g1b, fx1, fy1, bad);
-        float ey = err_from_g1<false>(c, rcp_w, g0, bl, g1c, fx2, fy2, bad);
-        float dx = fsub(ex, e0), dy = fsub(ey, e0);
-        float qx = div_by_const(dx, PF_GRAD_EPS, rcp_eps), qy = div_by_const(dy, PF_GRAD_EPS, rcp_eps);
-        bad = bad || !(in_div_range(dx) && in_div_range(dy));
-        if (bad) {                                   // rare: operands outside the verified range -> IEEE intrinsics
-            bool dummy = false;
+        unsigned tiny = 0xffffffffu;
+        float e0 = err_from_g1<false>(c, rcp_w, g0, bl, g1a, f.x, f.y, tiny);
+        float ex = err_from_g1<false>(c, rcp_w, g0, bl, g1b, fx1, fy1, tiny);
+        float ey = err_from_g1<false>(c, rcp_w, g0, bl, g1c, fx2, fy2, tiny);
+        const float2 d = upk(psub(pk(ex, ey), pk(e0, e0)));
+        float2 q = upk(div2_by_const(pk(d.x, d.y), PF_GRAD_EPS, rcp_eps));            // a difference of errors is never -0
+        tiny = min(tiny, min(tiny_key(fabsf(d.x)), tiny_key(fabsf(d.y))));
+        // operands outside the verified range of the branch-free sequences: tiny non-zero (key test), or huge / inf / NaN
+        // (every operand is bounded by the errors, so testing those is enough -- same test as the sweep kernel's)
+        const float vmax = fmaxf(fmaxf(fabsf(e0), fabsf(ex)), fabsf(ey));
+        const bool bad = (tiny < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f) || !(e0 == e0) || !(ex == ex) || !(ey == ey);
+        if (bad) {                                   // rare: IEEE intrinsics
+            unsigned dummy = 0;
             e0 = err_from_g1<true>(c, rcp_w, g0, bl, g1a, f.x, f.y, dummy);
             ex = err_from_g1<true>(c, rcp_w, g0, bl, g1b, fx1, fy1, dummy);
             ey = err_from_g1<true>(c, rcp_w, g0, bl, g1c, fx2, fy2, dummy);
-            qx = __fdiv_rn(fsub(ex, e0), PF_GRAD_EPS);
-            qy = __fdiv_rn(fsub(ey, e0), PF_GRAD_EPS);
+            q.x = __fdiv_rn(fsub(ex, e0), PF_GRAD_EPS);
+            q.y = __fdiv_rn(fsub(ey, e0), PF_GRAD_EPS);
         }
         A.x = e0;
-        A.y = fsub(f.x, fmul(PF_GRAD_STEP, qx));
-        A.z = fsub(f.y, fmul(PF_GRAD_STEP, qy));
+        A.y = fsub(f.x, fmul(PF_GRAD_STEP, q.x));
+        A.z = fsub(f.y, fmul(PF_GRAD_STEP, q.y));
     }
     const int j = a.dir > 0 ? y : h - 1 - y, i = a.dir > 0 ? x : w - 1 - x;
-    const int wb = j / a.R, g = j % a.R;
-    const size_t idx = ((size_t)wb * (w + a.R - 1) + (i + g)) * a.R + g;
+    const int wb = j >> a.logR, g = j & (a.R - 1);              // R = rows per sweep warp, a power of two
+    const size_t idx = (((size_t)wb * (w + a.R - 1) + (i + g)) << a.logR) + g;
     SweepRec r;
     r.a = A;
     r.b = make_float4(g0.x, g0.y, bl.x, bl.y);
