@@ -18,12 +18,12 @@ namespace pf {
 
 namespace {
 
-// One output pixel per thread: most launches are small pyramid levels whose duration is the latency of one thread.
 constexpr int TILE = 32;                 // tile width
-constexpr int BTH = 16;                  // blur tile height (512 threads)
+constexpr int BTH = 32;                  // blur tile height: 32 x 32 outputs per CTA, two per thread (rows ty and ty + 16)
+constexpr int BTY = 16;                  // blur thread rows (512 threads)
 constexpr int BR = 7;                    // radius of the 15-tap Gaussian
 constexpr int BW = TILE + 2 * BR;        // 46
-constexpr int BH = BTH + 2 * BR;         // 30
+constexpr int BH = BTH + 2 * BR;         // 46
 constexpr int MTH = 8;                   // median tile height (256 threads)
 constexpr int MR = 2;                    // radius of the 5x5 median
 constexpr int MW = TILE + 2 * MR;        // 36
@@ -39,62 +39,64 @@ __device__ __forceinline__ int reflect1_clamped(int p, int n) {
 }
 
 // 15x15 sigma 8 Gaussian of the 2-channel flow: row pass left-to-right over the 15 taps, column pass in the symmetric
-// form, both from shared memory.
+// form, both from shared memory.  The two channels of a flow vector go through identical arithmetic, so
+// every tap is ONE packed fp32x2 multiply and ONE packed add (pf_math.cuh) -- bit-identical to the scalar form at half
+// the instructions; 46 x 46 input tile -> 46 x 32 row pass -> 32 x 32 outputs (halo overhead 1.44x instead of 1.9x).
 template <int MODE>
-__global__ void __launch_bounds__(TILE * BTH)
+__global__ void __launch_bounds__(TILE * BTY)
 k_blur15(const float2* __restrict__ flow, float2* __restrict__ out, int h, int w, PrepArgs pa) {
     PF_GAUSS_TABLES
-    __shared__ float2 s_in[BH][BW];          // flow tile + halo, reflect-101 at the image border
-    __shared__ float2 s_row[BH][TILE];       // row pass
+    __shared__ f2p s_in[BH][BW];             // flow tile + halo, reflect-101 at the image border
+    __shared__ f2p s_row[BH][TILE];          // row pass
     const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * BTH;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    {   // tile + halo: each thread fetches (up to) 2 columns x 2 rows; reflect-101 indices computed once per thread.
+    const f2p* fl = reinterpret_cast<const f2p*>(flow);
+    {   // tile + halo: each thread fetches (up to) 2 columns x 3 rows; reflect-101 indices computed once per thread.
         // One reflection suffices for every position a valid output needs (w, h > 7); positions only reached by
         // out-of-image threads are clamped.
         const int gx0 = reflect1_clamped(x0 - BR + tx, w), gx1 = reflect1_clamped(x0 - BR + tx + TILE, w);
-        const int gy0 = reflect1_clamped(y0 - BR + ty, h), gy1 = reflect1_clamped(y0 - BR + ty + BTH, h);
-        const float2* r0 = flow + gy0 * w;
-        const float2* r1 = flow + gy1 * w;
-        s_in[ty][tx] = r0[gx0];
-        if (tx < BW - TILE) s_in[ty][tx + TILE] = r0[gx1];
-        if (ty < BH - BTH) {
-            s_in[ty + BTH][tx] = r1[gx0];
-            if (tx < BW - TILE) s_in[ty + BTH][tx + TILE] = r1[gx1];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int ly = ty + r * BTY;
+            if (ly < BH) {
+                const f2p* row = fl + reflect1_clamped(y0 - BR + ly, h) * w;
+                s_in[ly][tx] = row[gx0];
+                if (tx < BW - TILE) s_in[ly][tx + TILE] = row[gx1];
+            }
         }
     }
     __syncthreads();
-    for (int ly = ty; ly < BH; ly += BTH) {
-        float2 v = s_in[ly][tx];
-        float sx = fmul(kG15[7], v.x), sy = fmul(kG15[7], v.y);
 #pragma unroll
-        for (int i = 1; i < 15; ++i) {
-            v = s_in[ly][tx + i];
-            const float k = kG15[i < 7 ? 7 - i : i - 7];
-            sx = fadd(sx, fmul(k, v.x));
-            sy = fadd(sy, fmul(k, v.y));
+    for (int r = 0; r < 3; ++r) {
+        const int ly = ty + r * BTY;
+        if (ly < BH) {
+            f2p acc = pmuls(s_in[ly][tx], kG15[7]);
+#pragma unroll
+            for (int i = 1; i < 15; ++i) acc = padd(acc, pmuls(s_in[ly][tx + i], kG15[i < 7 ? 7 - i : i - 7]));
+            s_row[ly][tx] = acc;
         }
-        s_row[ly][tx] = make_float2(sx, sy);
     }
     __syncthreads();
-    const int x = x0 + tx, y = y0 + ty;
-    if (x >= w || y >= h) return;
-    const float2 cen = s_row[ty + BR][tx];
-    float sx = fmul(kG15[0], cen.x), sy = fmul(kG15[0], cen.y);
+    const int x = x0 + tx;
+    if (x >= w) return;
 #pragma unroll
-    for (int i = 1; i <= 7; ++i) {
-        const float2 a = s_row[ty + BR + i][tx], b = s_row[ty + BR - i][tx];
-        sx = fadd(sx, fmul(kG15[i], fadd(a.x, b.x)));
-        sy = fadd(sy, fmul(kG15[i], fadd(a.y, b.y)));
-    }
-    const size_t p = (size_t)y * w + x;
-    const float2 f = s_in[ty + BR][tx + BR];
-    if (MODE == MODE_DIFFUSE) {          // lowAlphaFlowDiffusion, CPU/PixFlow.hpp:395-404
-        const float d = fsub(1.0f, fmul(pa.alpha0[p], pa.alpha1[p]));
-        const float e = fsub(1.0f, d);
-        out[p] = make_float2(fadd(fmul(d, sx), fmul(e, f.x)), fadd(fmul(d, sy), fmul(e, f.y)));
-    } else {
-        out[p] = make_float2(sx, sy);
-        if (MODE == MODE_PREP) emit_record(pa, make_err_ctx(pa.G1, w, h), x, y, w, h, f, make_float2(sx, sy));
+    for (int r = 0; r < 2; ++r) {
+        const int ly = ty + r * BTY, y = y0 + ly;
+        if (y >= h) break;
+        f2p acc = pmuls(s_row[ly + BR][tx], kG15[0]);
+#pragma unroll
+        for (int i = 1; i <= 7; ++i) acc = padd(acc, pmuls(padd(s_row[ly + BR + i][tx], s_row[ly + BR - i][tx]), kG15[i]));
+        const size_t p = (size_t)y * w + x;
+        const f2p fp = s_in[ly + BR][tx + BR];
+        if (MODE == MODE_DIFFUSE) {          // lowAlphaFlowDiffusion, CPU/PixFlow.hpp:395-404
+            const float d = fsub(1.0f, fmul(pa.alpha0[p], pa.alpha1[p]));
+            const float e = fsub(1.0f, d);
+            out[p] = upk(padd(pmuls(acc, d), pmuls(fp, e)));
+        } else {
+            const float2 sv = upk(acc);
+            out[p] = sv;
+            if (MODE == MODE_PREP) emit_record(pa, make_err_ctx(pa.G1, w, h), x, y, w, h, upk(fp), sv);
+        }
     }
     (void)kG5; (void)kG3O; (void)kG3H;
 }
@@ -137,6 +139,7 @@ k_median5(const float2* __restrict__ src, float2* __restrict__ dst, const float2
 }
 
 inline dim3 blur_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + BTH - 1) / BTH); }
+const dim3 kBlurBlock(TILE, BTY);
 inline dim3 median_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + MTH - 1) / MTH); }
 
 PrepArgs make_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir) {
@@ -152,18 +155,18 @@ PrepArgs make_prep(const float* alpha0, const float* alpha1, const float2* G0, c
 
 void launch_blur15(const float2* flow, float2* blurred, int h, int w, cudaStream_t st) {
     PrepArgs pa = {};
-    k_blur15<MODE_PLAIN><<<blur_grid(w, h), dim3(TILE, BTH), 0, st>>>(flow, blurred, h, w, pa);
+    k_blur15<MODE_PLAIN><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, pa);
 }
 
 void launch_blur15_prep(const float2* flow, float2* blurred, int h, int w, const float* alpha0, const float* alpha1,
                         const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
-    k_blur15<MODE_PREP><<<blur_grid(w, h), dim3(TILE, BTH), 0, st>>>(flow, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir));
+    k_blur15<MODE_PREP><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir));
 }
 
 void launch_blur15_diffuse(const float2* flow, float2* out, int h, int w, const float* alpha0, const float* alpha1, cudaStream_t st) {
     PrepArgs pa = {};
     pa.alpha0 = alpha0; pa.alpha1 = alpha1;
-    k_blur15<MODE_DIFFUSE><<<blur_grid(w, h), dim3(TILE, BTH), 0, st>>>(flow, out, h, w, pa);
+    k_blur15<MODE_DIFFUSE><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, out, h, w, pa);
 }
 
 void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st) {
