@@ -71,11 +71,6 @@ PF_API int pf_prepare_bidirectional_batch(pf_engine* engine, int n,
                                           void* const* flows_l_to_r, size_t stride_lr,
                                           void* const* flows_r_to_l, size_t stride_rl);
 
-/* Farm-mode tuning: how many pairs of a batch share one workspace (= one pair of CUDA streams) and go through every kernel
- * together (gridDim.z).  0 (default) = automatic: ceil(n / 16), i.e. one pair per workspace up to 16 pairs in flight (the
- * device has 32 hardware work queues), more beyond.  Results do not depend on it. */
-PF_API int pf_set_pairs_per_workspace(pf_engine* engine, int pairs);
-
 /* Replaces NovelViewUtil::combineNovelViews(imageL, imageR, flowLtoR, flowRtoL, blend),
  * CPU/OpticalFlow.cpp:30-92 (generateNovelViewPoint :9-28 inlined).  out_bgra: rows x cols BGRA8. */
 PF_API int pf_combine_novel_views(pf_engine* engine,

@@ -31,7 +31,6 @@ SIGNATURES = {
     "pf_host_free": (_i, [_vp]),
     "pf_kernel_launch_count": (C.c_uint64, []),
     "pf_set_sweep_timing": (_i, [_vp, _i]),
-    "pf_set_pairs_per_workspace": (_i, [_vp, _i]),
     "pf_last_sweep_ms": (C.c_double, [_vp]),
     "pf_last_sweep_launches": (C.c_uint64, [_vp]),
     "pf_timer_start": (_i, [_vp]),

@@ -164,10 +164,6 @@ class PixFlow(OpticalFlowInterface):
         return ko
 
     # -- instrumentation used by bench.py --
-    def setPairsPerWorkspace(self, pairs):
-        """farm mode: pairs of a batch that share one pair of streams and run through every kernel together (0 = automatic)"""
-        _lib.check(self._lib.pf_set_pairs_per_workspace(self._h, int(pairs)))
-
     def setSweepTiming(self, enabled):
         _lib.check(self._lib.pf_set_sweep_timing(self._h, int(bool(enabled))))
 

@@ -101,7 +101,7 @@ struct Workspace {
     float* I[2] = {nullptr, nullptr};
     float* A[2] = {nullptr, nullptr};
     float* Ipre = nullptr;
-    float2* G_[2] = {nullptr, nullptr};           // row-major gradient pyramids (Ix, Iy)
+    float2* G[2] = {nullptr, nullptr};            // row-major gradient pyramids (Ix, Iy)
     float2* Gs[2] = {nullptr, nullptr};           // the same in the skewed layout (gathered by the sweeps)
     pf::SweepRec* rec[2] = {nullptr, nullptr};    // per direction: wavefront-packed records of the current sweep
     float2* bufA[2] = {nullptr, nullptr};         // per direction: flow ping
@@ -123,21 +123,15 @@ struct Workspace {
     uint64_t graph_launches = 0;                  // kernels per replay
     int graph_key = -1;                           // ndir | hint0 << 4 | hint1 << 8 | search_dist << 12
 
-    // Every per-pair buffer above is carved out of ONE arena per pair; a workspace holds `G` arenas back to back, so pair
-    // z's copy of any buffer is at byte offset z * arena_bytes from pair 0's pointer (the members above are pair 0's): the
-    // kernels process the G pairs of a workspace in lockstep with gridDim.z = G (pf_kernels.cuh, ZBatch).
-    int G = 1;
-    size_t arena_bytes = 0;
-    char* arena = nullptr;
-    template <class T> T* of_pair(T* p, int z) const { return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + (size_t)z * arena_bytes); }
-
     ~Workspace() { release(); }
     void release() {
         if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; graph_key = -1; }
-        cudaFree(arena); arena = nullptr;
         for (int k = 0; k < 2; ++k) {
-            in[k] = nullptr; I[k] = A[k] = nullptr; G_[k] = nullptr; Gs[k] = nullptr; rec[k] = nullptr;
-            bufA[k] = bufB[k] = blurred[k] = nullptr;
+            cudaFree(in[k]); cudaFree(I[k]); cudaFree(A[k]); cudaFree(G[k]); cudaFree(Gs[k]); cudaFree(rec[k]);
+            Gs[k] = nullptr; rec[k] = nullptr;
+            cudaFree(bufA[k]); cudaFree(bufB[k]); cudaFree(blurred[k]);
+            cudaFree(ratio[k]); cudaFree(bnd[k]); cudaFree(tickets[k]); cudaFree(out[k]);
+            in[k] = nullptr; I[k] = A[k] = nullptr; G[k] = nullptr; bufA[k] = bufB[k] = blurred[k] = nullptr;
             ratio[k] = nullptr; bnd[k] = nullptr; tickets[k] = nullptr; out[k] = nullptr;
             if (sDir[k]) cudaStreamDestroy(sDir[k]);
             if (evDone[k]) cudaEventDestroy(evDone[k]);
@@ -145,56 +139,35 @@ struct Workspace {
             for (auto e : sweepEv[k]) cudaEventDestroy(e);
             sweepEv[k].clear();
         }
-        cudaFree(merged); cudaFree(blend);
+        cudaFree(Ipre); cudaFree(merged); cudaFree(blend);
         Ipre = nullptr; merged = nullptr; blend = nullptr;
         if (evReady) cudaEventDestroy(evReady);
         sMain = nullptr; evReady = nullptr;
     }
 
-    int init(int rows, int cols, int pad, int idx, int group) {
+    int init(int rows, int cols, int pad, int idx = 0) {
         plan.build(rows, cols, pad);
-        G = group < 1 ? 1 : group;
         const Plan& p = plan;
         const size_t px0 = (size_t)p.dw * p.dh;
-        // arena layout (every buffer 512-byte aligned)
-        size_t off = 0;
-        auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 511) & ~(size_t)511; return o; };
-        size_t o_in[2], o_I[2], o_A[2], o_G[2], o_Gs[2], o_rec[2], o_bufA[2], o_bufB[2], o_blur[2], o_ratio[2], o_bnd[2], o_tick[2], o_out[2];
         for (int k = 0; k < 2; ++k) {
-            o_in[k] = take((size_t)rows * cols * 4);
-            o_I[k] = take(p.total_px * sizeof(float));
-            o_A[k] = take(p.total_px * sizeof(float));
-            o_G[k] = take(p.total_px * sizeof(float2));
-            o_Gs[k] = take(p.skew_total * sizeof(float2));
-            o_rec[k] = take(pf::sweep_rec_count(p.dh, p.dw) * sizeof(pf::SweepRec));
-            o_bufA[k] = take(px0 * sizeof(float2));
-            o_bufB[k] = take(px0 * sizeof(float2));
-            o_blur[k] = take(px0 * sizeof(float2));
-            o_ratio[k] = take(256);
-            o_bnd[k] = take((p.bnd_lines + 1) * sizeof(uint4));
-            o_tick[k] = take((size_t)p.L * 2 * sizeof(int));
-            o_out[k] = take((size_t)rows * cols * sizeof(float2));
-        }
-        const size_t o_Ipre = take(px0 * sizeof(float));
-        arena_bytes = off;
-        PF_CUDA(cudaMalloc(&arena, arena_bytes * (size_t)G));
-        for (int k = 0; k < 2; ++k) {
-            in[k] = reinterpret_cast<uint8_t*>(arena + o_in[k]);
-            I[k] = reinterpret_cast<float*>(arena + o_I[k]);
-            A[k] = reinterpret_cast<float*>(arena + o_A[k]);
-            G_[k] = reinterpret_cast<float2*>(arena + o_G[k]);
-            Gs[k] = reinterpret_cast<float2*>(arena + o_Gs[k]);
-            rec[k] = reinterpret_cast<pf::SweepRec*>(arena + o_rec[k]);
-            bufA[k] = reinterpret_cast<float2*>(arena + o_bufA[k]);
-            bufB[k] = reinterpret_cast<float2*>(arena + o_bufB[k]);
-            blurred[k] = reinterpret_cast<float2*>(arena + o_blur[k]);
-            ratio[k] = reinterpret_cast<float*>(arena + o_ratio[k]);
-            bnd[k] = reinterpret_cast<uint4*>(arena + o_bnd[k]);
-            tickets[k] = reinterpret_cast<int*>(arena + o_tick[k]);
-            out[k] = reinterpret_cast<float2*>(arena + o_out[k]);
+            PF_CUDA(cudaMalloc(&in[k], (size_t)rows * cols * 4));
+            PF_CUDA(cudaMalloc(&I[k], p.total_px * sizeof(float)));
+            PF_CUDA(cudaMalloc(&A[k], p.total_px * sizeof(float)));
+            PF_CUDA(cudaMalloc(&G[k], p.total_px * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&Gs[k], p.skew_total * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&rec[k], pf::sweep_rec_count(p.dh, p.dw) * sizeof(pf::SweepRec)));
+            PF_CUDA(cudaMalloc(&bufA[k], px0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&bufB[k], px0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&blurred[k], px0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&ratio[k], 256));
+            PF_CUDA(cudaMalloc(&bnd[k], (p.bnd_lines + 1) * sizeof(uint4)));
+            PF_CUDA(cudaMalloc(&tickets[k], (size_t)p.L * 2 * sizeof(int)));
+            PF_CUDA(cudaMalloc(&out[k], (size_t)rows * cols * sizeof(float2)));
             {
-                // Pairs in flight may get DIFFERENT stream priorities (PF_STREAM_PRIO: 0 off [default], 1 round-robin over the
-                // device's priority levels, 2 contiguous groups of 4).  Measured on B200: no gain (profiles/).
+                // Pairs in flight get DIFFERENT stream priorities (PF_STREAM_PRIO: 0 off, 1 round-robin over the
+                // device's priority levels, 2 contiguous groups of 4; measured on B200: no gain, default off): identical pairs launched together would
+                // otherwise march in lockstep -- all in their throughput-bound stencil kernels at the same time, then all
+                // in their latency-bound sweeps -- and the two kinds of work would never overlap.
                 static int mode = -1, least = 0, greatest = 0;
                 if (mode < 0) {
                     const char* ev = getenv("PF_STREAM_PRIO");
@@ -209,8 +182,8 @@ struct Workspace {
             }
             PF_CUDA(cudaEventCreateWithFlags(&evDone[k], cudaEventDisableTiming));
         }
-        Ipre = reinterpret_cast<float*>(arena + o_Ipre);
-        sMain = sDir[0];   // the shared front end runs on direction 0's stream: two streams (hardware queues) per workspace
+        PF_CUDA(cudaMalloc(&Ipre, px0 * sizeof(float)));
+        sMain = sDir[0];   // the shared front end runs on direction 0's stream: two streams (hardware queues) per pair
         PF_CUDA(cudaEventCreateWithFlags(&evReady, cudaEventDisableTiming));
         return PF_OK;
     }
@@ -224,7 +197,6 @@ struct pf_engine {
     int search_dist = 0;        // computeSearchDistance, CPU/PixFlow.hpp:153-155
     bool time_sweeps = false;
     bool use_graphs = true;     // PF_NO_GRAPHS=1 disables (per-kernel stream launches, used when timing the sweeps)
-    int pairs_per_workspace = 0; // 0: automatic (ceil(n / 16)), see pf_prepare_bidirectional_batch
     double last_sweep_ms = 0.0;
     uint64_t last_sweep_launches = 0;
     std::mutex mu;
@@ -240,17 +212,17 @@ struct pf_engine {
     }
 
     // workspace #idx for the given geometry (created or re-created on demand)
-    int workspace(int idx, int rows, int cols, int pad, Workspace** out, int group = 1) {
+    int workspace(int idx, int rows, int cols, int pad, Workspace** out) {
         while ((int)pool.size() <= idx) pool.push_back(nullptr);
         Workspace* w = pool[idx];
-        if (w && (w->plan.rows != rows || w->plan.cols != cols || w->plan.pad != pad || w->G < group)) {
+        if (w && (w->plan.rows != rows || w->plan.cols != cols || w->plan.pad != pad)) {
             std::lock_guard<std::mutex> cg(g_capture_mu);
             delete w; w = nullptr; pool[idx] = nullptr;
         }
         if (!w) {
             std::lock_guard<std::mutex> cg(g_capture_mu);
             w = new Workspace();
-            const int rc = w->init(rows, cols, pad, idx, group);
+            const int rc = w->init(rows, cols, pad, idx);
             if (rc != PF_OK) { delete w; pool[idx] = nullptr; return rc; }
             pool[idx] = w;
         }
@@ -273,10 +245,9 @@ cudaEvent_t next_sweep_event(Workspace& w, int d) {
 }
 
 // front end + pyramids + gradients for both images, on sMain (CPU/PixFlow.hpp:78-110, :284-294)
-int enqueue_shared(pf_engine* e, Workspace& w, int np, const uint8_t* img[2], const size_t stride[2]) {
+int enqueue_shared(pf_engine* e, Workspace& w, const uint8_t* img[2], const size_t stride[2]) {
     const Plan& p = w.plan;
     (void)e;
-    pf::ZBatchScope zscope(np, w.arena_bytes);
     for (int k = 0; k < 2; ++k) {
         pf::launch_frontend_resize(img[k], stride[k], p.rows, p.cols, p.pad, w.Ipre, w.A[k] + p.off[0], p.dh, p.dw, w.sMain);
         pf::launch_gauss5(w.Ipre, w.I[k] + p.off[0], p.dh, p.dw, w.sMain);
@@ -293,8 +264,8 @@ int enqueue_shared(pf_engine* e, Workspace& w, int np, const uint8_t* img[2], co
     }
     for (int l = 0; l < p.L; ++l)
         for (int k = 0; k < 2; ++k) {
-            pf::launch_gradient(w.I[k] + p.off[l], w.G_[k] + p.off[l], p.hs[l], p.ws[l], w.sMain);
-            pf::launch_skew_copy_f2(w.G_[k] + p.off[l], w.Gs[k] + p.skew_off[l], p.skew[l], w.sMain);
+            pf::launch_gradient(w.I[k] + p.off[l], w.G[k] + p.off[l], p.hs[l], p.ws[l], w.sMain);
+            pf::launch_skew_copy_f2(w.G[k] + p.off[l], w.Gs[k] + p.skew_off[l], p.skew[l], w.sMain);
             LAUNCHED(2);
         }
     PF_CUDA(cudaGetLastError());
@@ -303,16 +274,13 @@ int enqueue_shared(pf_engine* e, Workspace& w, int np, const uint8_t* img[2], co
 }
 
 // coarse-to-fine loop of one direction on sDir[d] (CPU/PixFlow.hpp:112-134); i0 = index of image I0
-int enqueue_direction(pf_engine* e, Workspace& w, int np, int d, int i0, int hint, float2* out, size_t out_stride) {
+int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float2* out, size_t out_stride) {
     const Plan& p = w.plan;
     const int i1 = 1 - i0;
     cudaStream_t st = w.sDir[d];
-    pf::ZBatchScope zscope(np, w.arena_bytes);        // every launch below covers the np pairs of this workspace
     PF_CUDA(cudaStreamWaitEvent(st, w.evReady, 0));
-    for (int z = 0; z < np; ++z) {
-        PF_CUDA(cudaMemsetAsync(w.of_pair(w.bnd[d], z), 0, (p.bnd_lines + 1) * sizeof(uint4), st));
-        PF_CUDA(cudaMemsetAsync(w.of_pair(w.tickets[d], z), 0, (size_t)p.L * 2 * sizeof(int), st));
-    }
+    PF_CUDA(cudaMemsetAsync(w.bnd[d], 0, (p.bnd_lines + 1) * sizeof(uint4), st));
+    PF_CUDA(cudaMemsetAsync(w.tickets[d], 0, (size_t)p.L * 2 * sizeof(int), st));
     float2* flow = w.bufA[d];
     float2* other = w.bufB[d];
     for (int l = p.L - 1; l >= 0; --l) {
@@ -325,8 +293,8 @@ int enqueue_direction(pf_engine* e, Workspace& w, int np, int d, int i0, int hin
             pf::launch_initial_flow(I0, I1, A0, A1, flow, w.ratio[d], h, wd, hint, e->search_dist, st);
             LAUNCHED(e->search_dist > 0 && hint != PF_HINT_UNKNOWN ? 2 : 1);
         }
-        const float2* G0 = w.G_[i0] + p.off[l];
-        const float2* G1 = w.G_[i1] + p.off[l];
+        const float2* G0 = w.G[i0] + p.off[l];
+        const float2* G1 = w.G[i1] + p.off[l];
         pf::Sweep2Args sa;
         sa.rec = w.rec[d];
         sa.G1s = w.Gs[i1] + p.skew_off[l];
@@ -400,40 +368,34 @@ int check_image_args(const void* p, size_t stride, int rows, int cols, size_t el
 
 // stage an input image: device pointers are used in place, host pointers are copied into ws.in[k]
 int stage_input(Workspace& w, int k, const void* img, size_t stride, const uint8_t** dptr, size_t* dstride, cudaStream_t st,
-                bool force_copy = false, int z = 0) {
+                bool force_copy = false) {
     if (!force_copy && is_device_ptr(img)) { *dptr = (const uint8_t*)img; *dstride = stride; return PF_OK; }
     const size_t dense = (size_t)w.plan.cols * 4;
-    uint8_t* dst = w.of_pair(w.in[k], z);
-    PF_CUDA(cudaMemcpy2DAsync(dst, dense, img, stride, dense, w.plan.rows, cudaMemcpyDefault, st));
-    *dptr = dst; *dstride = dense;
+    PF_CUDA(cudaMemcpy2DAsync(w.in[k], dense, img, stride, dense, w.plan.rows, cudaMemcpyDefault, st));
+    *dptr = w.in[k]; *dstride = dense;
     return PF_OK;
 }
 
-// the body shared by compute_flow / prepare / batch / novel_view for the np pairs of workspace w (asynchronous).
-// imgL/imgR/outs0/outs1 are arrays of np pointers (outs may hold NULLs); dimg/dflow describe pair 0 on return.
-int enqueue_group(pf_engine* e, Workspace& w, int np, const void* const* imgL, size_t strideL, const void* const* imgR, size_t strideR,
-                  int ndir, const int hints[2], void* const* outs0, void* const* outs1, const size_t ostrides[2],
-                  const uint8_t* dimg[2], size_t dstride[2], float2* dflow[2], size_t dfstride[2]) {
+// the body shared by compute_flow / prepare / batch / novel_view for ONE pair on workspace w (asynchronous)
+int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, const void* imgR, size_t strideR,
+                 int ndir, const int hints[2], void* outs[2], const size_t ostrides[2],
+                 const uint8_t* dimg[2], size_t dstride[2], float2* dflow[2], size_t dfstride[2]) {
     int rc;
-    void* const* outs[2] = {outs0, outs1};
-    const size_t fdense = (size_t)w.plan.cols * sizeof(float2);
-    if ((e->use_graphs && !e->time_sweeps) || np > 1) {
-        // ---- staged path: inputs -> arena staging buffers, one graph launch (or plain launches), outputs <- arena ----
+    if (e->use_graphs && !e->time_sweeps) {
+        // ---- graph path: inputs -> staging buffers, one graph launch, outputs <- workspace flow buffers ----
         cudaStream_t st = w.sDir[0];
-        for (int z = np - 1; z >= 0; --z) {
-            if ((rc = stage_input(w, 0, imgL[z], strideL, &dimg[0], &dstride[0], st, true, z)) != PF_OK) return rc;
-            if ((rc = stage_input(w, 1, imgR[z], strideR, &dimg[1], &dstride[1], st, true, z)) != PF_OK) return rc;
-        }
-        const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12) | (np << 20);
+        if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], st, true)) != PF_OK) return rc;
+        if ((rc = stage_input(w, 1, imgR, strideR, &dimg[1], &dstride[1], st, true)) != PF_OK) return rc;
+        const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12);
         bool have_graph = w.graph_key == key;
-        if (!have_graph && e->use_graphs && !e->time_sweeps) {
+        if (!have_graph) {
             std::lock_guard<std::mutex> cg(g_capture_mu);
             if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; w.graph_key = -1; }
             const uint64_t launched_before = g_launches.load();
             PF_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            rc = enqueue_shared(e, w, np, dimg, dstride);
+            rc = enqueue_shared(e, w, dimg, dstride);
             for (int d = 0; d < ndir && rc == PF_OK; ++d)
-                rc = enqueue_direction(e, w, np, d, d == 0 ? 0 : 1, hints[d], w.out[d], fdense);
+                rc = enqueue_direction(e, w, d, d == 0 ? 0 : 1, hints[d], w.out[d], (size_t)w.plan.cols * sizeof(float2));
             if (rc == PF_OK && ndir == 2) {      // join direction 1 back into the capturing stream
                 if (cudaEventRecord(w.evDone[1], w.sDir[1]) != cudaSuccess || cudaStreamWaitEvent(st, w.evDone[1], 0) != cudaSuccess)
                     rc = PF_ERR_CUDA;
@@ -458,9 +420,9 @@ int enqueue_group(pf_engine* e, Workspace& w, int np, const void* const* imgL, s
             }
         }
         if (!have_graph) {
-            if ((rc = enqueue_shared(e, w, np, dimg, dstride)) != PF_OK) return rc;
+            if ((rc = enqueue_shared(e, w, dimg, dstride)) != PF_OK) return rc;
             for (int d = 0; d < ndir; ++d)
-                if ((rc = enqueue_direction(e, w, np, d, d == 0 ? 0 : 1, hints[d], w.out[d], fdense)) != PF_OK) return rc;
+                if ((rc = enqueue_direction(e, w, d, d == 0 ? 0 : 1, hints[d], w.out[d], (size_t)w.plan.cols * sizeof(float2))) != PF_OK) return rc;
             if (ndir == 2) {
                 PF_CUDA(cudaEventRecord(w.evDone[1], w.sDir[1]));
                 PF_CUDA(cudaStreamWaitEvent(st, w.evDone[1], 0));
@@ -471,41 +433,29 @@ int enqueue_group(pf_engine* e, Workspace& w, int np, const void* const* imgL, s
         }
         for (int d = 0; d < ndir; ++d) {
             dflow[d] = w.out[d];
-            dfstride[d] = fdense;
-            for (int z = 0; z < np; ++z)
-                if (outs[d] && outs[d][z])
-                    PF_CUDA(cudaMemcpy2DAsync(outs[d][z], ostrides[d], w.of_pair(w.out[d], z), fdense, fdense, w.plan.rows, cudaMemcpyDefault, st));
+            dfstride[d] = (size_t)w.plan.cols * sizeof(float2);
+            if (outs[d])
+                PF_CUDA(cudaMemcpy2DAsync(outs[d], ostrides[d], w.out[d], dfstride[d], (size_t)w.plan.cols * sizeof(float2),
+                                          w.plan.rows, cudaMemcpyDefault, st));
         }
         PF_CUDA(cudaEventRecord(w.evDone[0], st));
         if (ndir == 2) PF_CUDA(cudaEventRecord(w.evDone[1], st));
         return PF_OK;
     }
-    // ---- one pair, plain stream launches, device pointers used in place (sweep timing / PF_NO_GRAPHS) ----
-    if ((rc = stage_input(w, 0, imgL[0], strideL, &dimg[0], &dstride[0], w.sMain)) != PF_OK) return rc;
-    if ((rc = stage_input(w, 1, imgR[0], strideR, &dimg[1], &dstride[1], w.sMain)) != PF_OK) return rc;
-    if ((rc = enqueue_shared(e, w, 1, dimg, dstride)) != PF_OK) return rc;
+    if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], w.sMain)) != PF_OK) return rc;
+    if ((rc = stage_input(w, 1, imgR, strideR, &dimg[1], &dstride[1], w.sMain)) != PF_OK) return rc;
+    if ((rc = enqueue_shared(e, w, dimg, dstride)) != PF_OK) return rc;
     for (int d = 0; d < ndir; ++d) {
-        void* o = outs[d] ? outs[d][0] : nullptr;
-        const bool dev_out = o && is_device_ptr(o);
-        dflow[d] = dev_out ? (float2*)o : w.out[d];
-        dfstride[d] = dev_out ? ostrides[d] : fdense;
-        if ((rc = enqueue_direction(e, w, 1, d, d == 0 ? 0 : 1, hints[d], dflow[d], dfstride[d])) != PF_OK) return rc;
-        if (o && !dev_out)
-            PF_CUDA(cudaMemcpy2DAsync(o, ostrides[d], w.out[d], dfstride[d], fdense, w.plan.rows, cudaMemcpyDeviceToHost, w.sDir[d]));
+        const bool dev_out = outs[d] && is_device_ptr(outs[d]);
+        dflow[d] = dev_out ? (float2*)outs[d] : w.out[d];
+        dfstride[d] = dev_out ? ostrides[d] : (size_t)w.plan.cols * sizeof(float2);
+        if ((rc = enqueue_direction(e, w, d, d == 0 ? 0 : 1, hints[d], dflow[d], dfstride[d])) != PF_OK) return rc;
+        if (outs[d] && !dev_out)
+            PF_CUDA(cudaMemcpy2DAsync(outs[d], ostrides[d], w.out[d], dfstride[d], (size_t)w.plan.cols * sizeof(float2),
+                                      w.plan.rows, cudaMemcpyDeviceToHost, w.sDir[d]));
         PF_CUDA(cudaEventRecord(w.evDone[d], w.sDir[d]));
     }
     return PF_OK;
-}
-
-// one pair (compute_flow, novel_view)
-int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, const void* imgR, size_t strideR,
-                 int ndir, const int hints[2], void* outs[2], const size_t ostrides[2],
-                 const uint8_t* dimg[2], size_t dstride[2], float2* dflow[2], size_t dfstride[2]) {
-    const void* Ls[1] = {imgL};
-    const void* Rs[1] = {imgR};
-    void* o0[1] = {outs[0]};
-    void* o1[1] = {outs[1]};
-    return enqueue_group(e, w, 1, Ls, strideL, Rs, strideR, ndir, hints, o0, o1, ostrides, dimg, dstride, dflow, dfstride);
 }
 
 int sync_pair(Workspace& w, int ndir) {
@@ -584,13 +534,6 @@ void pf_engine_destroy(pf_engine* e) {
         }
         delete e;
     }
-}
-
-int pf_set_pairs_per_workspace(pf_engine* e, int pairs) {
-    if (!e || pairs < 0 || pairs > 64) return fail(PF_ERR_INVALID_ARGUMENT, "pairs per workspace must be in [0, 64]");
-    std::lock_guard<std::mutex> lk(e->mu);
-    e->pairs_per_workspace = pairs;
-    return PF_OK;
 }
 
 int pf_set_sweep_timing(pf_engine* e, int enabled) {
@@ -674,21 +617,14 @@ int pf_prepare_bidirectional_batch(pf_engine* e, int n, const void* const* Ls, s
     std::vector<Workspace*> used;
     const auto t_begin = std::chrono::steady_clock::now();
     const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};   // CPU/OpticalFlow.cpp:130-139
-    // Pairs per workspace: a workspace drives two streams and the device has 32 hardware work queues, so at most 16
-    // workspaces run truly concurrently; beyond 16 pairs, G pairs share a workspace and go through every kernel together
-    // (gridDim.z = G).  PF_GROUP overrides.
-    int G = (n + 15) / 16;
-    { static int forced = -1; if (forced < 0) { const char* ev = getenv("PF_GROUP"); forced = ev ? atoi(ev) : 0; } if (forced > 0) G = forced; }
-    if (e->pairs_per_workspace > 0) G = e->pairs_per_workspace;
-    if (G > n) G = n;
-    const size_t ostr[2] = {slr, srl};
-    for (int i0 = 0, wi = 0; i0 < n; i0 += G, ++wi) {
-        const int np = n - i0 < G ? n - i0 : G;
+    for (int i = 0; i < n; ++i) {
         Workspace* w;
-        if ((rc = e->workspace(wi, rows, cols, pad, &w, G)) != PF_OK) return rc;
+        if ((rc = e->workspace(i, rows, cols, pad, &w)) != PF_OK) return rc;
         used.push_back(w);
+        void* outs[2] = {lr[i], rl[i]};
+        const size_t ostr[2] = {slr, srl};
         const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
-        if ((rc = enqueue_group(e, *w, np, Ls + i0, sl, Rs + i0, sr, 2, hints, lr + i0, rl + i0, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
+        if ((rc = enqueue_pair(e, *w, Ls[i], sl, Rs[i], sr, 2, hints, outs, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
     }
     const auto t_enq = std::chrono::steady_clock::now();
     for (Workspace* w : used)

@@ -44,11 +44,8 @@ __device__ __forceinline__ int reflect1_clamped(int p, int n) {
 // the instructions; 46 x 46 input tile -> 46 x 32 row pass -> 32 x 32 outputs (halo overhead 1.44x instead of 1.9x).
 template <int MODE>
 __global__ void __launch_bounds__(TILE * BTY)
-k_blur15(const float2* __restrict__ flow, float2* __restrict__ out, int h, int w, PrepArgs pa, size_t zs) {
+k_blur15(const float2* __restrict__ flow, float2* __restrict__ out, int h, int w, PrepArgs pa) {
     PF_GAUSS_TABLES
-    PF_ZOFF(flow); PF_ZOFF(out);
-    if (MODE != MODE_PLAIN) { PF_ZOFF(pa.alpha0); PF_ZOFF(pa.alpha1); }
-    if (MODE == MODE_PREP) { PF_ZOFF(pa.G0); PF_ZOFF(pa.G1); PF_ZOFF(pa.rec); }
     __shared__ f2p s_in[BH][BW];             // flow tile + halo, reflect-101 at the image border
     __shared__ f2p s_row[BH][TILE];          // row pass
     const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * BTH;
@@ -107,9 +104,7 @@ k_blur15(const float2* __restrict__ flow, float2* __restrict__ out, int h, int w
 // medianBlur(32FC2, 5), replicate border, from a shared-memory tile (+ the records of the coming sweep)
 template <int MODE>
 __global__ void __launch_bounds__(TILE * MTH)
-k_median5(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ blurred, int h, int w, PrepArgs pa, size_t zs) {
-    PF_ZOFF(src); PF_ZOFF(dst);
-    if (MODE == MODE_PREP) { PF_ZOFF(blurred); PF_ZOFF(pa.alpha0); PF_ZOFF(pa.alpha1); PF_ZOFF(pa.G0); PF_ZOFF(pa.G1); PF_ZOFF(pa.rec); }
+k_median5(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ blurred, int h, int w, PrepArgs pa) {
     __shared__ float2 s_in[MH][MW + 1];
     const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * MTH;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -143,9 +138,9 @@ k_median5(const float2* __restrict__ src, float2* __restrict__ dst, const float2
     if (MODE == MODE_PREP) emit_record(pa, make_err_ctx(pa.G1, w, h), x, y, w, h, m, blurred[p]);
 }
 
-inline dim3 blur_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + BTH - 1) / BTH, zbatch().n); }
+inline dim3 blur_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + BTH - 1) / BTH); }
 const dim3 kBlurBlock(TILE, BTY);
-inline dim3 median_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + MTH - 1) / MTH, zbatch().n); }
+inline dim3 median_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + MTH - 1) / MTH); }
 
 PrepArgs make_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir) {
     PrepArgs pa;
@@ -160,28 +155,28 @@ PrepArgs make_prep(const float* alpha0, const float* alpha1, const float2* G0, c
 
 void launch_blur15(const float2* flow, float2* blurred, int h, int w, cudaStream_t st) {
     PrepArgs pa = {};
-    k_blur15<MODE_PLAIN><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, pa, zbatch().stride);
+    k_blur15<MODE_PLAIN><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, pa);
 }
 
 void launch_blur15_prep(const float2* flow, float2* blurred, int h, int w, const float* alpha0, const float* alpha1,
                         const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
-    k_blur15<MODE_PREP><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir), zbatch().stride);
+    k_blur15<MODE_PREP><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir));
 }
 
 void launch_blur15_diffuse(const float2* flow, float2* out, int h, int w, const float* alpha0, const float* alpha1, cudaStream_t st) {
     PrepArgs pa = {};
     pa.alpha0 = alpha0; pa.alpha1 = alpha1;
-    k_blur15<MODE_DIFFUSE><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, out, h, w, pa, zbatch().stride);
+    k_blur15<MODE_DIFFUSE><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, out, h, w, pa);
 }
 
 void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st) {
     PrepArgs pa = {};
-    k_median5<MODE_PLAIN><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, nullptr, h, w, pa, zbatch().stride);
+    k_median5<MODE_PLAIN><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, nullptr, h, w, pa);
 }
 
 void launch_median5_prep(const float2* src, float2* dst, const float2* blurred, int h, int w, const float* alpha0,
                          const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
-    k_median5<MODE_PREP><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir), zbatch().stride);
+    k_median5<MODE_PREP><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir));
 }
 
 }  // namespace pf

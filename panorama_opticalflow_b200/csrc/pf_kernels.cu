@@ -8,13 +8,7 @@
 
 namespace pf {
 
-ZBatch& zbatch() {
-    static thread_local ZBatch zb = {1, 0};
-    return zb;
-}
-
-// 2-D grid over the image, z = pairs per launch
-static inline dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y, zbatch().n); }
+static inline dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
 
 // ====================================================================================================
 // front end
@@ -27,8 +21,7 @@ __device__ __forceinline__ int sat_short_rint(float v) {
 __global__ void __launch_bounds__(256)
 k_frontend_resize(const uint8_t* __restrict__ bgra, size_t stride, int rows, int cols, int pad,
                   float* __restrict__ grey, float* __restrict__ alpha, int dh, int dw,
-                  double scale_x, double scale_y, size_t zs) {
-    PF_ZOFF(bgra); PF_ZOFF(grey); PF_ZOFF(alpha);
+                  double scale_x, double scale_y) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
@@ -91,13 +84,12 @@ void launch_frontend_resize(const uint8_t* bgra, size_t stride, int rows, int co
     const double scale_x = 1.0 / ((double)dw / (double)pcols);
     const double scale_y = 1.0 / ((double)dh / (double)rows);
     dim3 b(32, 8);
-    k_frontend_resize<<<grid2d(dw, dh, b), b, 0, st>>>(bgra, stride, rows, cols, pad, grey, alpha, dh, dw, scale_x, scale_y, zbatch().stride);
+    k_frontend_resize<<<grid2d(dw, dh, b), b, 0, st>>>(bgra, stride, rows, cols, pad, grey, alpha, dh, dw, scale_x, scale_y);
 }
 
 __global__ void __launch_bounds__(256)
-k_gauss5(const float* __restrict__ src, float* __restrict__ dst, int h, int w, size_t zs) {
+k_gauss5(const float* __restrict__ src, float* __restrict__ dst, int h, int w) {
     PF_GAUSS_TABLES
-    PF_ZOFF(src); PF_ZOFF(dst);
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
@@ -120,7 +112,7 @@ k_gauss5(const float* __restrict__ src, float* __restrict__ dst, int h, int w, s
 
 void launch_gauss5(const float* src, float* dst, int h, int w, cudaStream_t st) {
     dim3 b(32, 8);
-    k_gauss5<<<grid2d(w, h, b), b, 0, st>>>(src, dst, h, w, zbatch().stride);
+    k_gauss5<<<grid2d(w, h, b), b, 0, st>>>(src, dst, h, w);
 }
 
 // ====================================================================================================
@@ -135,7 +127,7 @@ __device__ __forceinline__ void linear_coord_x(int d, double scale, int sw, int&
 // Resize coordinates are computed in double precision exactly like OpenCV does -- once per CTA column / row into
 // shared memory instead of once per pixel (the FP64 sequence was the bulk of this kernel's instructions).
 __global__ void __launch_bounds__(256)
-k_pyr_down(PlaneSet ps, int nplanes, int sh, int sw, int dh, int dw, double scale_x, double scale_y, size_t zs) {
+k_pyr_down(PlaneSet ps, int sh, int sw, int dh, int dw, double scale_x, double scale_y) {
     __shared__ int s_xs[32];
     __shared__ float s_xf[32];
     __shared__ int s_y0[8], s_y1[8];
@@ -156,10 +148,8 @@ k_pyr_down(PlaneSet ps, int nplanes, int sh, int sw, int dh, int dw, double scal
     }
     __syncthreads();
     if (x >= dw || y >= dh) return;
-    const int plane = blockIdx.z % nplanes;
-    const size_t zoff = (size_t)(blockIdx.z / nplanes) * zs;          // z = pair * nplanes + plane
-    const float* __restrict__ src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ps.src[plane]) + zoff);
-    float* __restrict__ dst = reinterpret_cast<float*>(reinterpret_cast<char*>(ps.dst[plane]) + zoff);
+    const float* __restrict__ src = ps.src[blockIdx.z];
+    float* __restrict__ dst = ps.dst[blockIdx.z];
     const int s = s_xs[threadIdx.x];
     const float f = s_xf[threadIdx.x], fy = s_fy[threadIdx.y];
     const float* S0 = src + s_y0[threadIdx.y] * sw;
@@ -179,8 +169,8 @@ void launch_pyr_down(const PlaneSet& ps, int nplanes, int sh, int sw, int dh, in
     const double scale_y = 1.0 / ((double)dh / (double)sh);
     dim3 b(32, 8);
     dim3 g = grid2d(dw, dh, b);
-    g.z = nplanes * zbatch().n;
-    k_pyr_down<<<g, b, 0, st>>>(ps, nplanes, sh, sw, dh, dw, scale_x, scale_y, zbatch().stride);
+    g.z = nplanes;
+    k_pyr_down<<<g, b, 0, st>>>(ps, sh, sw, dh, dw, scale_x, scale_y);
 }
 
 // ====================================================================================================
@@ -190,9 +180,8 @@ void launch_pyr_down(const PlaneSet& ps, int nplanes, int sh, int sw, int dh, in
 // blur reflect-101 of the Sobel image; both index maps stay within 2 pixels of the output position, so every tap is a
 // shared-memory read at (global index - tile origin).
 __global__ void __launch_bounds__(256)
-k_gradient(const float* __restrict__ I, float2* __restrict__ G, int h, int w, size_t zs) {
+k_gradient(const float* __restrict__ I, float2* __restrict__ G, int h, int w) {
     PF_GAUSS_TABLES
-    PF_ZOFF(I); PF_ZOFF(G);
     __shared__ float s_I[12][36 + 1];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
@@ -237,7 +226,7 @@ k_gradient(const float* __restrict__ I, float2* __restrict__ G, int h, int w, si
 
 void launch_gradient(const float* I, float2* G, int h, int w, cudaStream_t st) {
     dim3 b(32, 8);
-    k_gradient<<<grid2d(w, h, b), b, 0, st>>>(I, G, h, w, zbatch().stride);
+    k_gradient<<<grid2d(w, h, b), b, 0, st>>>(I, G, h, w);
 }
 
 // ====================================================================================================
@@ -245,8 +234,7 @@ void launch_gradient(const float* I, float2* G, int h, int w, cudaStream_t st) {
 // ====================================================================================================
 __global__ void __launch_bounds__(256)
 k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, float2* __restrict__ dst, int dh, int dw,
-                 double scale_x, double scale_y, size_t zs) {
-    PF_ZOFF(src); PF_ZOFF(dst);
+                 double scale_x, double scale_y) {
     __shared__ int s_sx[32], s_sy[8];
     __shared__ float s_ca[32][4], s_cb[8][4];
     const int x = blockIdx.x * 32 + threadIdx.x;
@@ -299,7 +287,7 @@ void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int d
     const double scale_x = 1.0 / ((double)dw / (double)sw);
     const double scale_y = 1.0 / ((double)dh / (double)sh);
     dim3 b(32, 8);
-    k_upsample_cubic<<<grid2d(dw, dh, b), b, 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y, zbatch().stride);
+    k_upsample_cubic<<<grid2d(dw, dh, b), b, 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y);
 }
 
 // ====================================================================================================
@@ -310,9 +298,8 @@ void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int d
 // the 3x3 sigma-1 row and column passes run from shared memory.
 __global__ void __launch_bounds__(256)
 k_tail(const float2* __restrict__ src, int sh, int sw, int rows, int pcols, int pad, int cols,
-       float2* __restrict__ out, size_t out_stride, double scale_x, double scale_y, size_t zs) {
+       float2* __restrict__ out, size_t out_stride, double scale_x, double scale_y) {
     PF_GAUSS_TABLES
-    PF_ZOFF(src); PF_ZOFF(out);
     __shared__ int s_xs[34];
     __shared__ float s_xf[34];
     __shared__ int s_y0[10], s_y1[10];
@@ -376,7 +363,7 @@ void launch_tail(const float2* flow0, int sh, int sw, int rows, int pcols, int p
     const double scale_x = 1.0 / ((double)pcols / (double)sw);
     const double scale_y = 1.0 / ((double)rows / (double)sh);
     dim3 b(32, 8);
-    k_tail<<<grid2d(cols, rows, b), b, 0, st>>>(flow0, sh, sw, rows, pcols, pad, cols, out, out_stride, scale_x, scale_y, zbatch().stride);
+    k_tail<<<grid2d(cols, rows, b), b, 0, st>>>(flow0, sh, sw, rows, pcols, pad, cols, out, out_stride, scale_x, scale_y);
 }
 
 // ====================================================================================================
@@ -384,9 +371,8 @@ void launch_tail(const float2* flow0, int sh, int sw, int rows, int pcols, int p
 // ====================================================================================================
 // computeIntensityRatio: sequential fp32 sums in raster order (order-dependent -> one thread)
 __global__ void k_intensity_ratio(const float* __restrict__ I0, const float* __restrict__ a0,
-                                  const float* __restrict__ I1, const float* __restrict__ a1, int n, float* ratio, size_t zs) {
+                                  const float* __restrict__ I1, const float* __restrict__ a1, int n, float* ratio) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    PF_ZOFF(I0); PF_ZOFF(a0); PF_ZOFF(I1); PF_ZOFF(a1); PF_ZOFF(ratio);
     float sumL = 0.0f, sumR = 0.0f;
     for (int i = 0; i < n; ++i) {
         const float al = fmul(a0[i], a1[i]);
@@ -426,8 +412,7 @@ __device__ float patch_error(const float* __restrict__ i0, const float* __restri
 __global__ void __launch_bounds__(128)
 k_adjust_initial_flow(const float* __restrict__ I0, const float* __restrict__ I1,
                       const float* __restrict__ a0, const float* __restrict__ a1, float2* __restrict__ flow,
-                      const float* __restrict__ ratio_p, int h, int w, int bx, int by, int bw, int bh, int dist, size_t zs) {
-    PF_ZOFF(I0); PF_ZOFF(I1); PF_ZOFF(a0); PF_ZOFF(a1); PF_ZOFF(flow); PF_ZOFF(ratio_p);
+                      const float* __restrict__ ratio_p, int h, int w, int bx, int by, int bw, int bh, int dist) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
@@ -460,10 +445,10 @@ void launch_initial_flow(const float* I0, const float* I1, const float* alpha0, 
         case 3: bx = -dist; by = -ortho; bw = dist + 1; bh = thick; break;    // LEFT
         case 4: bx = -ortho; by = -dist; bw = thick; bh = dist + 1; break;    // UP
         }
-        k_intensity_ratio<<<dim3(1, 1, zbatch().n), 32, 0, st>>>(I0, alpha0, I1, alpha1, h * w, ratio, zbatch().stride);
+        k_intensity_ratio<<<1, 32, 0, st>>>(I0, alpha0, I1, alpha1, h * w, ratio);
     }
     dim3 b(32, 4);
-    k_adjust_initial_flow<<<grid2d(w, h, b), b, 0, st>>>(I0, I1, alpha0, alpha1, flow, ratio, h, w, bx, by, bw, bh, dist, zbatch().stride);
+    k_adjust_initial_flow<<<grid2d(w, h, b), b, 0, st>>>(I0, I1, alpha0, alpha1, flow, ratio, h, w, bx, by, bw, bh, dist);
 }
 
 // ====================================================================================================
@@ -525,7 +510,7 @@ void launch_combine(const uint8_t* imageL, size_t strideL, const uint8_t* imageR
                     const float* blend, size_t strideB, int rows, int cols,
                     uint8_t* out, size_t strideOut, cudaStream_t st) {
     dim3 b(32, 8);
-    k_combine<<<dim3((cols + b.x - 1) / b.x, (rows + b.y - 1) / b.y), b, 0, st>>>(imageL, strideL, imageR, strideR, flowLR, strideLR, flowRL, strideRL,
+    k_combine<<<grid2d(cols, rows, b), b, 0, st>>>(imageL, strideL, imageR, strideR, flowLR, strideLR, flowRL, strideRL,
                                                   blend, strideB, rows, cols, out, strideOut);
 }
 

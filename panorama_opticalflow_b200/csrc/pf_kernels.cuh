@@ -7,22 +7,6 @@
 
 namespace pf {
 
-// ---- pairs per launch ("z-batching") ---------------------------------------------------------------------------------
-// One stream of kernels can process n independent pairs of identical geometry in lockstep: every per-pair buffer of pair z
-// lives at the same offset inside that pair's arena, i.e. at byte offset z * stride from pair 0's pointer, so each flow
-// kernel takes pair 0's pointers plus the stride and uses gridDim.z (blockIdx.z) for the pair.  This is how the engine
-// keeps more pairs in flight than the 32 hardware work queues allow as independent streams.  The setting is thread-local
-// and read by every launcher of the flow path below (the stitching launchers always process one canvas).
-struct ZBatch { int n; size_t stride; };
-ZBatch& zbatch();
-struct ZBatchScope {           // RAII: set for the calls made in this scope
-    ZBatch saved;
-    ZBatchScope(int n, size_t stride) : saved(zbatch()) { zbatch().n = n; zbatch().stride = stride; }
-    ~ZBatchScope() { zbatch() = saved; }
-};
-// inside a kernel: rebase a pointer parameter to this CTA's pair
-#define PF_ZOFF(p) p = reinterpret_cast<decltype(p)>(reinterpret_cast<uintptr_t>(p) + (uintptr_t)blockIdx.z * zs)
-
 // ---- front end (CPU/PixFlow.hpp:78-103) -----------------------------------------------------------
 // Cubic 1/2 downscale of a BGRA8 image whose columns are read through the circular pad of
 // NovelViewGeneratorAsymmetricFlow::prepare (CPU/OpticalFlow.cpp:113-126): padded column c maps to source

@@ -77,8 +77,7 @@ __device__ __forceinline__ void store_tile_skewed(const T* tile, T* __restrict__
 }
 
 __global__ void __launch_bounds__(256)
-k_skew_copy_f2(const float2* __restrict__ src, float2* __restrict__ dst, Skew s, size_t zs) {
-    PF_ZOFF(src); PF_ZOFF(dst);
+k_skew_copy_f2(const float2* __restrict__ src, float2* __restrict__ dst, Skew s) {
     __shared__ float2 tile[32 * 32];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     const int lx = threadIdx.x;
@@ -93,8 +92,8 @@ k_skew_copy_f2(const float2* __restrict__ src, float2* __restrict__ dst, Skew s,
 }
 
 void launch_skew_copy_f2(const float2* src, float2* dst, const Skew& s, cudaStream_t st) {
-    dim3 b(32, 8), g((s.w + 31) / 32, (s.h + 31) / 32, zbatch().n);
-    k_skew_copy_f2<<<g, b, 0, st>>>(src, dst, s, zbatch().stride);
+    dim3 b(32, 8), g((s.w + 31) / 32, (s.h + 31) / 32);
+    k_skew_copy_f2<<<g, b, 0, st>>>(src, dst, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -120,7 +119,7 @@ size_t sweep_rec_count(int h, int w) {
 
 // stand-alone form (the production path fuses this into the blur / median kernels, pf_fused.cu)
 __global__ void __launch_bounds__(256)
-k_sweep_prep(const float2* __restrict__ blurred, const float2* __restrict__ flow, int h, int w, PrepArgs pa) {   // one pair
+k_sweep_prep(const float2* __restrict__ blurred, const float2* __restrict__ flow, int h, int w, PrepArgs pa) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
@@ -592,9 +591,8 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
 // front do not occupy registers and shared memory while they would only be waiting for their turn.
 template <int DIR, int POSX, int P>
 __global__ void __launch_bounds__(SweepGeom<P>::THREADS)
-k_sweep6(Sweep2Args a, size_t zs) {
+k_sweep6(Sweep2Args a) {
     typedef SweepGeom<P> G;
-    PF_ZOFF(a.rec); PF_ZOFF(a.G1s); PF_ZOFF(a.flow); PF_ZOFF(a.boundary); PF_ZOFF(a.ticket);
     __shared__ SweepSmem<P> sm;
     const int nblocks = (a.s.h + G::ROWS_PER_CTA - 1) / G::ROWS_PER_CTA;
     for (;;) {
@@ -673,9 +671,9 @@ static void launch_sweep_p(const Sweep2Args& a, int dir, cudaStream_t st) {
         attr_done[dev] = true;
     }
     if (dir > 0) {
-        if (a.s.posx) k_sweep6<1, 1, P><<<dim3(ncta, 1, zbatch().n), G::THREADS, pad, st>>>(a, zbatch().stride); else k_sweep6<1, 0, P><<<dim3(ncta, 1, zbatch().n), G::THREADS, pad, st>>>(a, zbatch().stride);
+        if (a.s.posx) k_sweep6<1, 1, P><<<ncta, G::THREADS, pad, st>>>(a); else k_sweep6<1, 0, P><<<ncta, G::THREADS, pad, st>>>(a);
     } else {
-        if (a.s.posx) k_sweep6<-1, 1, P><<<dim3(ncta, 1, zbatch().n), G::THREADS, pad, st>>>(a, zbatch().stride); else k_sweep6<-1, 0, P><<<dim3(ncta, 1, zbatch().n), G::THREADS, pad, st>>>(a, zbatch().stride);
+        if (a.s.posx) k_sweep6<-1, 1, P><<<ncta, G::THREADS, pad, st>>>(a); else k_sweep6<-1, 0, P><<<ncta, G::THREADS, pad, st>>>(a);
     }
 }
 

@@ -168,26 +168,3 @@ def test_stream_path_equals_graph_path(orc, engine_search):
         assert_bit_equal(b, c, "stream path")
     again = engine_search.prepareBidirectional(L, R)     # replay of the cached graph
     assert_bit_equal(again[0], want[0], "graph replay")
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("group", [2, 3, 5])
-def test_grouped_batch_equals_singles(group):
-    """pairs that share a workspace go through every kernel together (gridDim.z): same bits as one pair at a time"""
-    import panorama_opticalflow_b200 as pf
-    from panorama_opticalflow_b200 import synth
-    eng = pf.makeOpticalFlowByName("pixflow_search_20")
-    try:
-        pairs = [synth.make_pair(90, 130, seed=30 + i, amplitude=12.0, sparse=(i == 2)) for i in range(5)]
-        singles = [eng.prepareBidirectional(L, R) for L, R in pairs]
-        eng.setPairsPerWorkspace(group)
-        bLR, bRL = eng.prepareBidirectionalBatch([p[0] for p in pairs], [p[1] for p in pairs])
-        for i in range(5):
-            assert_bit_equal(bLR[i], singles[i][0], "group %d batch[%d] flowLtoR" % (group, i))
-            assert_bit_equal(bRL[i], singles[i][1], "group %d batch[%d] flowRtoL" % (group, i))
-        # a single call afterwards reuses the grouped workspace
-        eng.setPairsPerWorkspace(0)
-        again = eng.prepareBidirectional(*pairs[3])
-        assert_bit_equal(again[0], singles[3][0], "single after grouped")
-    finally:
-        eng.close()
