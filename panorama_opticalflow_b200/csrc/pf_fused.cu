@@ -146,7 +146,7 @@ PrepArgs make_prep(const float* alpha0, const float* alpha1, const float2* G0, c
     PrepArgs pa;
     pa.alpha0 = alpha0; pa.alpha1 = alpha1; pa.G0 = G0; pa.G1 = G1; pa.rec = rec;
     pa.R = 32 / sweep_lanes_per_row();
-    pa.logR = pa.R == 4 ? 2 : (pa.R == 16 ? 4 : 5);
+    pa.logR = pa.R == 4 ? 2 : (pa.R == 8 ? 3 : (pa.R == 16 ? 4 : 5));
     pa.dir = dir;
     return pa;
 }

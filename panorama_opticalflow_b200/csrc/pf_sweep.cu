@@ -134,7 +134,7 @@ void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G
     PrepArgs pa;
     pa.alpha0 = alpha0; pa.alpha1 = alpha1; pa.G0 = G0; pa.G1 = G1; pa.rec = rec;
     pa.R = 32 / sweep_lanes_per_row();
-    pa.logR = pa.R == 4 ? 2 : (pa.R == 16 ? 4 : 5);
+    pa.logR = pa.R == 4 ? 2 : (pa.R == 8 ? 3 : (pa.R == 16 ? 4 : 5));
     pa.dir = dir;
     k_sweep_prep<<<g, b, 0, st>>>(blurred, flow, h, w, pa);
 }
@@ -142,7 +142,10 @@ void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G
 // ---------------------------------------------------------------------------------------------------------
 // the wavefront sweep
 // ---------------------------------------------------------------------------------------------------------
-constexpr int SW_PREFETCH_GATHER = 4;          // steps ahead for the L1 warm-up of the gradient gather
+#ifndef PF_SW_PREFETCH
+#define PF_SW_PREFETCH 4
+#endif
+constexpr int SW_PREFETCH_GATHER = PF_SW_PREFETCH;          // steps ahead for the L1 warm-up of the gradient gather
 constexpr int SW_LL_RING = 64;                 // entries of a shared-memory LL ring (power of two)
 constexpr int SW_PROGRESS_EVERY = 8;           // consumer publishes its progress every 8 columns
 
@@ -151,8 +154,8 @@ constexpr int SW_PROGRESS_EVERY = 8;           // consumer publishes its progres
 // per pixel and independent chains for the in-order scheduler to interleave.
 template <int P> struct SweepGeom {
     static constexpr int ROWS = 32 / P;                       // rows per warp
-    static constexpr int NQ = P == 8 ? 1 : (P == 2 ? 3 : 6);  // evaluations per lane
-    static constexpr int WARPS = P == 8 ? 8 : (P == 2 ? 4 : 2);   // compute warps per CTA (+ 1 poller warp)
+    static constexpr int NQ = P == 8 ? 1 : (P == 4 ? 2 : (P == 2 ? 3 : 6));   // evaluations per lane
+    static constexpr int WARPS = P == 8 ? 8 : (P == 4 ? 8 : (P == 2 ? 4 : 2));    // compute warps per CTA (+ 1 poller warp)
     static constexpr int ROWS_PER_CTA = ROWS * WARPS;
     static constexpr int THREADS = (WARPS + 1) * 32;
     static constexpr int DEPTH = P == 8 ? 8 : 4;              // cp.async groups in flight (steps of lookahead)
@@ -329,6 +332,27 @@ __device__ __forceinline__ void eval_err3(const SweepConst& k, float xf, float y
     v[0] = err_from_taps<SLOW>(k, t0, c0.xR, c0.yR, g0, bl, fx0, fy0, tiny);
     v[1] = err_from_taps<SLOW>(k, t1, c1.xR, c1.yR, g0, bl, fx1, fy0, tiny);
     v[2] = err_from_taps<SLOW>(k, t2, c2.xR, c2.yR, g0, bl, fx0, fy2, tiny);
+}
+
+// P = 4: two probes of ONE candidate on one lane -- (0,0) and (eps,0) on the even lane of the candidate's lane pair, (0,eps)
+// twice on the odd one (the duplicate is free in SIMT and keeps the lanes in step)
+template <int POSX, bool SLOW>
+__device__ __forceinline__ void eval_err2(const SweepConst& k, float xf, float yf, float2 g0, float2 bl, float2 cand, bool odd,
+                                          float v[2], unsigned& tiny) {
+    const float fxa = fadd(cand.x, 0.0f), fya = fadd(cand.y, odd ? PF_GRAD_EPS : 0.0f);
+    const float fxb = fadd(cand.x, odd ? 0.0f : PF_GRAD_EPS), fyb = fya;
+    const SkewCell c0 = skew_cell<POSX>(k, fadd(xf, fxa), fadd(yf, fya));
+    const SkewCell c1 = skew_cell<POSX>(k, fadd(xf, fxb), fadd(yf, fyb));
+    const SkewCoef t0 = skew_gather<POSX>(k, c0.gi);
+    {   // warm L1 with the anti-diagonal the gather reaches a few steps from now (asynchronous copy into a scratch slot)
+        int pi = c0.gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
+        pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
+        cp_async16(k.touch, k.G1s + pi);
+    }
+    SkewCoef t1 = t0;
+    if (__any_sync(0xffffffffu, c1.gi != c0.gi)) t1 = skew_gather<POSX>(k, c1.gi);     // the probe crossed a texel boundary
+    v[0] = err_from_taps<SLOW>(k, t0, c0.xR, c0.yR, g0, bl, fxa, fya, tiny);
+    v[1] = err_from_taps<SLOW>(k, t1, c1.xR, c1.yR, g0, bl, fxb, fyb, tiny);
 }
 
 // One candidate's gradient step (CPU/PixFlow.hpp:321, :364-386) from its three errors {E, E(+dx), E(+dy)}: r = cand - step * dE/eps
@@ -520,6 +544,8 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
                     unsigned t1 = 0xffffffffu;
                     v[0] = eval_err<POSX, SLOW>(k, xf, yf, g0, bl, fadd(cand.x, offx8), fadd(cand.y, offy8), t1);
                     tkey = min(tkey, t1);
+                } else if constexpr (P == 4) {
+                    eval_err2<POSX, SLOW>(k, xf, yf, g0, bl, sub >= 2 ? up : res, (sub & 1) != 0, v, tkey);
                 } else if constexpr (P == 2) {
                     eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, sub != 0 ? up : res, v, tkey);
                 } else {
@@ -540,6 +566,17 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
                     const float2 other = make_float2(ox, oy);
                     out = select_result(sub == 0 ? v[0] : oe, sub == 0 ? mine : other, sub == 0 ? oe : v[0], sub == 0 ? other : mine,
                                         i > 0, j > 0, A);
+                } else if constexpr (P == 4) {
+                    // lanes {0,1} of a row hold the left candidate's {E, E+dx | E+dy}, lanes {2,3} the up candidate's: the even
+                    // lane of each pair finishes its candidate, then all four lanes fetch both {E, r.x, r.y}
+                    const float edy = __shfl_xor_sync(full, v[0], 1);
+                    const float e3[3] = {v[0], v[1], edy};
+                    const float2 mine = finish_candidate<SLOW>(k, e3, sub >= 2 ? up : res, t2);
+                    t2 = (sub & 1) ? 0xffffffffu : t2;               // the odd lanes' finish is a don't-care
+                    const float eL = __shfl_sync(full, v[0], gbase), eU = __shfl_sync(full, v[0], gbase + 2);
+                    const float2 rL = make_float2(__shfl_sync(full, mine.x, gbase), __shfl_sync(full, mine.y, gbase));
+                    const float2 rU = make_float2(__shfl_sync(full, mine.x, gbase + 2), __shfl_sync(full, mine.y, gbase + 2));
+                    out = select_result(eL, rL, eU, rU, i > 0, j > 0, A);
                 } else {
                     // every lane of the row gets the six errors {L, L+dx, L+dy, U, U+dx, U+dy}
                     float e6[6];
@@ -615,14 +652,14 @@ int sweep_lanes_per_row() {
     if (p == 0) {
         const char* e = getenv("PF_SWEEP_LANES");
         const int v = e ? atoi(e) : 2;
-        p = (v == 1 || v == 2 || v == 8) ? v : 2;
+        p = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 2;
     }
     return p;
 }
 
 static int rows_per_cta() {
     const int p = sweep_lanes_per_row();
-    return p == 8 ? SweepGeom<8>::ROWS_PER_CTA : (p == 2 ? SweepGeom<2>::ROWS_PER_CTA : SweepGeom<1>::ROWS_PER_CTA);
+    return p == 8 ? SweepGeom<8>::ROWS_PER_CTA : (p == 4 ? SweepGeom<4>::ROWS_PER_CTA : (p == 2 ? SweepGeom<2>::ROWS_PER_CTA : SweepGeom<1>::ROWS_PER_CTA));
 }
 
 size_t sweep2_boundary_lines(int h, int w, bool) {
@@ -685,6 +722,7 @@ void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st) {
     switch (sweep_lanes_per_row()) {
     case 1: launch_sweep_p<1>(a, dir, st); break;
     case 2: launch_sweep_p<2>(a, dir, st); break;
+    case 4: launch_sweep_p<4>(a, dir, st); break;
     default: launch_sweep_p<8>(a, dir, st); break;
     }
 }
