@@ -35,7 +35,7 @@ METRIC = "Mpix/s bidirectional flow (2000x4000 pair)"
 UNIT = "Mpix/s"
 SWEEP_BYTES_PER_PX = 48          # alpha0, alpha1, I0x, I0y, I1x, I1y, blurred(8) read + flow r/w(16)
 PAIR_BYTES_PER_PX = 762.15       # whole pair, both directions + warp/blend
-SWEEP_DRAM_BYTES_PER_LAUNCH = 11.1e6   # measured once with ncu (see roofline.traffic_source); algorithmic avg is 15.0e6
+SWEEP_DRAM_BYTES_PER_LAUNCH = 13.18e6  # measured once with ncu (see roofline.traffic_source); algorithmic avg is 15.0e6
 
 
 def pyramid_levels(rows, cols, pad):
@@ -262,7 +262,7 @@ def run_b200(args, rank, world, local_rank):
     achieved = sweep_bytes / (sweep_ms / 1e3) / 1e9 if sweep_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_sweep (wavefront Gauss-Seidel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": SWEEP_DRAM_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 184 sweep launches of one 4000x2000 pair (ncu, profiles/r1_launches_p2_4000x2000.csv)",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 148 sweep launches of one 4000x2000 pair (ncu, profiles/r1_launches_head_4000x2000.csv)",
                 "algorithmic_bytes_per_launch_avg": sweep_bytes / max(1, sweep_launches),
                 "avg_launch_ms": sweep_ms / max(1, sweep_launches), "launches_per_step": sweep_launches,
                 "note": "sum of per-launch durations (launches of different directions/pairs overlap in time)",
