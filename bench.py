@@ -24,6 +24,8 @@ import time
 # One hardware work queue per stream of the engine (3 streams per pair in flight): without this, streams share
 # queues and kernels of independent pairs serialise behind each other.  Must be set before CUDA initialises.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# stdout carries exactly one JSON line: NCCL's banner / debug lines (NCCL_DEBUG=VERSION|INFO) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 

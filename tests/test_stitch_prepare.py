@@ -188,3 +188,32 @@ def test_four_input_frontend_vs_oracle(orc, engine_low):
     wL, wR = orc.four_input_frontend(*imgs)
     assert_bit_equal(L, wL, "colorImageL")
     assert_bit_equal(R, wR, "colorImageR")
+
+
+@pytest.mark.gpu
+def test_four_input_single_pass_like_main(orc, engine_search):
+    """CPU_4Input/main.cpp:54-113: input preparation, then the same single stitching pass."""
+    import panorama_opticalflow_b200 as pf
+    from panorama_opticalflow_b200 import synth
+    rows, cols = 400, 336
+    base = [synth.make_pair(rows, cols, seed=40 + k, amplitude=10.0, sparse=False)[0] for k in range(4)]
+    x = np.mgrid[0:rows, 0:cols][1]
+    spans = [(0, 120), (80, 200), (170, 260), (230, 336)]          # 1.tif .. 4.tif: L = 1 + 3, R = 2 + 4, neighbours overlap
+    imgs = []
+    for k, (a, b) in enumerate(spans):
+        im = base[k].copy()
+        im[..., 3] = np.where((x >= a) & (x < b), 255, 0)
+        im[im[..., 3] == 0] = 0
+        imgs.append(im)
+    imgs[0][rows // 2, 50:53, 3] = 0         # columns blanked by the middle-row test only
+    L, R = pf.api.four_input_frontend(engine_search, *imgs)
+    wL, wR = orc.four_input_frontend(*imgs)
+    assert_bit_equal(L, wL, "colorImageL")
+    assert_bit_equal(R, wR, "colorImageR")
+    assert not L[:, 50:53].any()
+    final = pf.stitch_iteration(engine_search, L, R)
+    want, inter = orc.stitch_iteration(wL, wR, 20)
+    assert (inter["map"] == 150).sum() > 1000
+    d = np.abs(final.astype(int) - want.astype(int))
+    assert d[..., :3].max() <= 1 and d[..., 3].max() == 0
+    assert np.array_equal(final[inter["map"] != 150], want[inter["map"] != 150])
