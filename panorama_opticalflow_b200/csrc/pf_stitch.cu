@@ -106,6 +106,12 @@ __device__ __forceinline__ int ld_volatile_global_s32(const int* p) {
 __device__ __forceinline__ void st_volatile_global_s32(int* p, int v) {
     asm volatile("st.volatile.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+// release store at gpu scope: everything this thread observed before it (including, through the preceding bar.sync, the
+// other threads' stores of the block) is visible to whoever reads the new value -- one instruction on one thread instead
+// of a __threadfence() per writer (fence.acq_rel.gpu also invalidates the SM's L1, B300_MICROARCH.md)
+__device__ __forceinline__ void st_release_global_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
 // OpenCV's RowSum<float,double> over one window row S[0 .. n+k-2] -> D[0 .. n-1] (stride ds)
 __device__ __forceinline__ void box_row_sums(const float* S, int n, int k, double* D, int ds) {
@@ -155,17 +161,18 @@ k_stitch_block_blur(BlockBlurArgs a) {
         const float* mrow = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.mdis) + (size_t)y * a.strideD);
         for (int bx = tid; bx < a.nbx; bx += nt) flag[bx] = mrow[bx * a.step] > fstep ? 1 : 0;
         __syncthreads();
-        int bx = 0;
+        int bx = 0, seen = 0;
         while (bx < a.nbx && !flag[bx]) ++bx;
         if (tid == 0) st_volatile_global_s32(a.progress + by, bx);         // leading unflagged blocks are complete
         while (bx < a.nbx) {
             // ---- wait for the rows above ----
             const int need = min(bx + a.rx + 1, a.nbx);
-            for (int j = tid; j < a.ry; j += nt)
-                if (by - 1 - j >= 0)
-                    while (ld_volatile_global_s32(a.progress + by - 1 - j) < need) __nanosleep(64);
-            __threadfence();
-            __syncthreads();
+            if (tid < a.ry && by - 1 - tid >= 0)             // thread j watches row by-1-j; the last value seen is kept, so a
+                while (seen < need) {                         // row that is far ahead is polled once, not once per block
+                    seen = ld_volatile_global_s32(a.progress + by - 1 - tid);
+                    if (seen < need) __nanosleep(64);
+                }
+            __syncthreads();       // no fence: the window is read with ld.cg (L2), never from this SM's L1
             // ---- window of the current image ----
             const int x = bx * a.step;
             for (int idx = tid; idx < nr * nr; idx += nt) {
@@ -185,12 +192,11 @@ k_stitch_block_blur(BlockBlurArgs a) {
                     __stcg(o, __double2float_rn(__dmul_rn(s0, scale)));
                     SUM = __dsub_rn(s0, rs[yy * a.step + i]);
                 }
-                __threadfence();
             }
             __syncthreads();
             ++bx;
             while (bx < a.nbx && !flag[bx]) ++bx;
-            if (tid == 0) st_volatile_global_s32(a.progress + by, bx);
+            if (tid == 0) st_release_global_s32(a.progress + by, bx);
         }
     }
 }
@@ -202,35 +208,39 @@ k_stitch_block_blur(BlockBlurArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int BOX_KMAX = 64;
 
+// Row pass: one lane per image row, sliding along it; the loads of a lane walk one cache line per 32 steps (L1-resident) and
+// are independent of the running sum, so the compiler pipelines them ahead of the dependent double-precision chain; the
+// sums are transposed through shared memory so that the global stores are coalesced.
 __global__ void __launch_bounds__(32)
 k_box_rows(const float* __restrict__ src, size_t stride, int rows, int cols, int k, double* __restrict__ rs) {
-    __shared__ float tile[32][32 + BOX_KMAX + 1];       // extended columns [c0-1, c0+31+k) of 32 rows
     __shared__ double outt[32][33];
     const int lane = threadIdx.x, r0 = blockIdx.x * 32, an = k / 2;
-    const int n = 32 + k;
+    const float* __restrict__ S = reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + (size_t)min(r0 + lane, rows - 1) * stride);
+    auto at = [&](int xe) -> double { return (double)S[reflect101_dev(xe - an, cols)]; };     // extended column xe
+    auto at_fast = [&](int xe) -> double { return (double)S[xe - an]; };                        // when 0 <= xe - an < cols
     double s = 0.0;
+    if (k > 5) for (int j = 0; j < k; ++j) s = __dadd_rn(s, at(j));
     for (int c0 = 0; c0 < cols; c0 += 32) {
-        for (int rr = 0; rr < 32; ++rr) {
-            const int row = min(r0 + rr, rows - 1);
-            const float* p = reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + (size_t)row * stride);
-            for (int cc = lane; cc < n; cc += 32) tile[rr][cc] = p[reflect101_dev(c0 - 1 - an + cc, cols)];
-        }
-        __syncwarp();
-        const float* S = &tile[lane][1];                 // S[i] = extended column c0 + i
+        const bool interior = c0 - 1 - an >= 0 && c0 + 31 + k - an < cols;     // every tap of this chunk inside the row
         if (k <= 5) {
+#pragma unroll 8
             for (int i = 0; i < 32; ++i) {
-                double t = (double)S[i];
-                for (int j = 1; j < k; ++j) t = __dadd_rn(t, (double)S[i + j]);
+                const int c = c0 + i;
+                double t = interior ? at_fast(c) : at(c);
+                for (int j = 1; j < k; ++j) t = __dadd_rn(t, interior ? at_fast(c + j) : at(c + j));
                 outt[lane][i] = t;
+            }
+        } else if (interior) {
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const int c = c0 + i;
+                s = __dadd_rn(s, __dsub_rn(at_fast(c - 1 + k), at_fast(c - 1)));
+                outt[lane][i] = s;
             }
         } else {
             for (int i = 0; i < 32; ++i) {
-                if (c0 + i == 0) {
-                    s = 0.0;
-                    for (int j = 0; j < k; ++j) s = __dadd_rn(s, (double)S[j]);
-                } else {
-                    s = __dadd_rn(s, __dsub_rn((double)S[i - 1 + k], (double)S[i - 1]));
-                }
+                const int c = c0 + i;
+                if (c > 0) s = __dadd_rn(s, __dsub_rn(at(c - 1 + k), at(c - 1)));
                 outt[lane][i] = s;
             }
         }
@@ -241,7 +251,9 @@ k_box_rows(const float* __restrict__ src, size_t stride, int rows, int cols, int
     }
 }
 
-__global__ void __launch_bounds__(128)
+// Column pass: one thread per column, running sum down the rows (interior rows without the border arithmetic, unrolled so
+// that the loads run ahead of the dependent chain).
+__global__ void __launch_bounds__(64)
 k_box_cols(const double* __restrict__ rs, int rows, int cols, int k, float* __restrict__ dst, size_t stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cols) return;
@@ -249,14 +261,44 @@ k_box_cols(const double* __restrict__ rs, int rows, int cols, int k, float* __re
     const double scale = 1.0 / (double)(k * k);
     double SUM = 0.0;
     for (int r = 0; r < k - 1; ++r) SUM = __dadd_rn(SUM, rs[(size_t)reflect101_dev(r - an, rows) * cols + i]);
-#pragma unroll 4
-    for (int y = 0; y < rows; ++y) {
-        const double sp = rs[(size_t)reflect101_dev(y + k - 1 - an, rows) * cols + i];
-        const double sm = rs[(size_t)reflect101_dev(y - an, rows) * cols + i];
+    auto step = [&](int y, double sp, double sm) {
         const double s0 = __dadd_rn(SUM, sp);
         reinterpret_cast<float*>(reinterpret_cast<char*>(dst) + (size_t)y * stride)[i] = __double2float_rn(__dmul_rn(s0, scale));
         SUM = __dsub_rn(s0, sm);
+    };
+    const int y_lo = min(an, rows), y_hi = max(y_lo, rows - (k - 1 - an));      // interior: 0 <= y-an and y+k-1-an < rows
+    for (int y = 0; y < y_lo; ++y)
+        step(y, rs[(size_t)reflect101_dev(y + k - 1 - an, rows) * cols + i], rs[(size_t)reflect101_dev(y - an, rows) * cols + i]);
+    const double* __restrict__ pp = rs + (size_t)(y_lo + k - 1 - an) * cols + i;
+    const double* __restrict__ pm = rs + (size_t)(y_lo - an) * cols + i;
+    // software-pipelined: the 2 x 8 loads of the next group are in flight while the current group's dependent chain runs
+    constexpr int U = 8;
+    double cp[U], cm[U];
+    int y = y_lo;
+    if (y + U <= y_hi) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { cp[u] = pp[(size_t)u * cols]; cm[u] = pm[(size_t)u * cols]; }
+        for (; y + 2 * U <= y_hi; y += U) {
+            double np_[U], nm_[U];
+            pp += (size_t)U * cols; pm += (size_t)U * cols;
+#pragma unroll
+            for (int u = 0; u < U; ++u) { np_[u] = pp[(size_t)u * cols]; nm_[u] = pm[(size_t)u * cols]; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) step(y + u, cp[u], cm[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) { cp[u] = np_[u]; cm[u] = nm_[u]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) step(y + u, cp[u], cm[u]);
+        y += U;
+        pp += (size_t)U * cols; pm += (size_t)U * cols;
     }
+    for (; y < y_hi; ++y) {
+        step(y, *pp, *pm);
+        pp += cols; pm += cols;
+    }
+    for (int y = y_hi; y < rows; ++y)
+        step(y, rs[(size_t)reflect101_dev(y + k - 1 - an, rows) * cols + i], rs[(size_t)reflect101_dev(y - an, rows) * cols + i]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -369,6 +411,7 @@ int launch_stitch_blend_smooth(float* blend, size_t strideB, const float* mdis, 
     a.nbx = (cols - 1) / step; a.nby = (rows - 1) / step;
     const int an = k1 / 2;
     a.rx = (an + step - 1) / step; a.ry = a.rx;
+    if (a.ry > 128) return 0;
     double* rs = reinterpret_cast<double*>(scratch);
     int* sync = reinterpret_cast<int*>(rs + (size_t)rows * cols);
     a.progress = sync + 16; a.ticket = sync;
@@ -383,7 +426,7 @@ int launch_stitch_blend_smooth(float* blend, size_t strideB, const float* mdis, 
     const int ncta = a.nby < 592 ? a.nby : 592;
     if (a.nby > 0 && a.nbx > 0) k_stitch_block_blur<<<ncta, 128, smem, st>>>(a);
     k_box_rows<<<(rows + 31) / 32, 32, 0, st>>>(blend, strideB, rows, cols, k2, rs);
-    k_box_cols<<<(cols + 127) / 128, 128, 0, st>>>(rs, rows, cols, k2, blend, strideB);
+    k_box_cols<<<(cols + 63) / 64, 64, 0, st>>>(rs, rows, cols, k2, blend, strideB);
     return 3;
 }
 
