@@ -115,6 +115,7 @@ struct Workspace {
     float* blend = nullptr;
     cudaStream_t sMain = nullptr, sDir[2] = {nullptr, nullptr};
     cudaEvent_t evReady = nullptr, evDone[2] = {nullptr, nullptr};
+    cudaEvent_t evIn = nullptr;                   // host inputs staged (recorded on the engine's copy stream)
     std::vector<cudaEvent_t> sweepEv[2];          // optional timing events
     size_t nSweepEv[2] = {0, 0};
     // the whole pair pipeline (front end -> both directions -> join) captured once as a CUDA graph and replayed
@@ -142,7 +143,8 @@ struct Workspace {
         cudaFree(Ipre); cudaFree(merged); cudaFree(blend);
         Ipre = nullptr; merged = nullptr; blend = nullptr;
         if (evReady) cudaEventDestroy(evReady);
-        sMain = nullptr; evReady = nullptr;
+        if (evIn) cudaEventDestroy(evIn);
+        sMain = nullptr; evReady = nullptr; evIn = nullptr;
     }
 
     int init(int rows, int cols, int pad, int idx = 0) {
@@ -185,6 +187,7 @@ struct Workspace {
         PF_CUDA(cudaMalloc(&Ipre, px0 * sizeof(float)));
         sMain = sDir[0];   // the shared front end runs on direction 0's stream: two streams (hardware queues) per pair
         PF_CUDA(cudaEventCreateWithFlags(&evReady, cudaEventDisableTiming));
+        PF_CUDA(cudaEventCreateWithFlags(&evIn, cudaEventDisableTiming));
         return PF_OK;
     }
 };
@@ -202,6 +205,10 @@ struct pf_engine {
     std::mutex mu;
     std::vector<Workspace*> pool;
     cudaStream_t sTimer = nullptr;
+    // Host inputs of all pairs are staged through ONE copy stream, in pair order: issued on the pairs' own streams the 2n
+    // uploads of a batch interleave on the DMA engine and every pair's inputs complete only when all have, which idles the
+    // GPU for the whole upload; in FIFO order pair 0 starts computing after its own 2 images have arrived.
+    cudaStream_t sCopy = nullptr;
     cudaEvent_t evT0 = nullptr, evT1 = nullptr;
 
     ~pf_engine() {
@@ -209,6 +216,7 @@ struct pf_engine {
         if (evT0) cudaEventDestroy(evT0);
         if (evT1) cudaEventDestroy(evT1);
         if (sTimer) cudaStreamDestroy(sTimer);
+        if (sCopy) cudaStreamDestroy(sCopy);
     }
 
     // workspace #idx for the given geometry (created or re-created on demand)
@@ -384,8 +392,14 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
     if (e->use_graphs && !e->time_sweeps) {
         // ---- graph path: inputs -> staging buffers, one graph launch, outputs <- workspace flow buffers ----
         cudaStream_t st = w.sDir[0];
-        if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], st, true)) != PF_OK) return rc;
-        if ((rc = stage_input(w, 1, imgR, strideR, &dimg[1], &dstride[1], st, true)) != PF_OK) return rc;
+        const bool hostL = !is_device_ptr(imgL), hostR = !is_device_ptr(imgR);
+        if ((hostL || hostR) && !e->sCopy) PF_CUDA(cudaStreamCreateWithFlags(&e->sCopy, cudaStreamNonBlocking));
+        if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], hostL ? e->sCopy : st, true)) != PF_OK) return rc;
+        if ((rc = stage_input(w, 1, imgR, strideR, &dimg[1], &dstride[1], hostR ? e->sCopy : st, true)) != PF_OK) return rc;
+        if (hostL || hostR) {
+            PF_CUDA(cudaEventRecord(w.evIn, e->sCopy));
+            PF_CUDA(cudaStreamWaitEvent(st, w.evIn, 0));
+        }
         const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12);
         bool have_graph = w.graph_key == key;
         if (!have_graph) {
