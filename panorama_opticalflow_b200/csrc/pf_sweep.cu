@@ -336,12 +336,13 @@ __device__ __forceinline__ void eval_err3(const SweepConst& k, float xf, float y
     const SkewCell c1 = skew_cell<POSX>(k, fadd(xf, fx1), fadd(yf, fy0));
     const SkewCell c2 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy2));
 #if PF_SWEEP_GATHER8
-    const float2* p0 = k.G1s + c0.gi;
-    const float2* p1 = p0 + k.pitch;             // anti-diagonal +1: (x0,y0+1) and (x0+1,y0) are adjacent
-    const float2* p2 = p1 + k.pitch;             // +2: (x0,y0+2), (x0+1,y0+1), (x0+2,y0)
-    const int i3 = c0.gi + 3 * k.pitch;          // +3: (x0+1,y0+2), (x0+2,y0+1); may lie past the array for the last cells
-    const f2p F00 = pk(__ldg(p0)), F10 = pk(__ldg(p1 + (POSX ? 1 : 0))), F01 = pk(__ldg(p1 + (POSX ? 0 : 1))), F11 = pk(__ldg(p2 + 1));
-    const int i2 = c0.gi + 2 * k.pitch;          // the extra texels of the very last cell may lie past the array: clamped (unused there)
+    // element indices in 32 bits, one independent 64-bit address per load (no pointer-increment carry chains on the critical path)
+    const int i1 = c0.gi + k.pitch;              // anti-diagonal +1: (x0,y0+1) and (x0+1,y0) are adjacent
+    const int i2 = i1 + k.pitch;                 // +2: (x0,y0+2), (x0+1,y0+1), (x0+2,y0)
+    const int i3 = i2 + k.pitch;                 // +3: (x0+1,y0+2), (x0+2,y0+1)
+    const f2p F00 = pk(__ldg(k.G1s + c0.gi)), F10 = pk(__ldg(k.G1s + i1 + (POSX ? 1 : 0))), F01 = pk(__ldg(k.G1s + i1 + (POSX ? 0 : 1)));
+    const f2p F11 = pk(__ldg(k.G1s + i2 + 1));
+    // the extra texels of the last cells may lie past the array: clamped (their values are unused there)
     const f2p X0 = pk(__ldg(k.G1s + min(i2 + (POSX ? 2 : 0), k.g1s_last))), Y0 = pk(__ldg(k.G1s + min(i2 + (POSX ? 0 : 2), k.g1s_last)));
     const f2p X1 = pk(__ldg(k.G1s + min(i3 + (POSX ? 2 : 1), k.g1s_last))), Y1 = pk(__ldg(k.G1s + min(i3 + (POSX ? 1 : 2), k.g1s_last)));
     {   // warm L1 with the anti-diagonal the gather reaches a few steps from now (asynchronous copy into a scratch slot)
