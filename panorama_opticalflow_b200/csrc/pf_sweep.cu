@@ -142,6 +142,9 @@ void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G
 // ---------------------------------------------------------------------------------------------------------
 // the wavefront sweep
 // ---------------------------------------------------------------------------------------------------------
+#ifndef PF_SWEEP_WARPS2
+#define PF_SWEEP_WARPS2 4
+#endif
 #ifndef PF_SW_PREFETCH
 #define PF_SW_PREFETCH 4
 #endif
@@ -155,7 +158,7 @@ constexpr int SW_PROGRESS_EVERY = 8;           // consumer publishes its progres
 template <int P> struct SweepGeom {
     static constexpr int ROWS = 32 / P;                       // rows per warp
     static constexpr int NQ = P == 8 ? 1 : (P == 4 ? 2 : (P == 2 ? 3 : 6));   // evaluations per lane
-    static constexpr int WARPS = P == 8 ? 8 : (P == 4 ? 8 : (P == 2 ? 4 : 2));    // compute warps per CTA (+ 1 poller warp)
+    static constexpr int WARPS = P == 8 ? 8 : (P == 4 ? 8 : (P == 2 ? PF_SWEEP_WARPS2 : 2));    // compute warps per CTA (+ 1 poller warp)
     static constexpr int ROWS_PER_CTA = ROWS * WARPS;
     static constexpr int THREADS = (WARPS + 1) * 32;
     static constexpr int DEPTH = P == 8 ? 8 : 4;              // cp.async groups in flight (steps of lookahead)
