@@ -176,13 +176,16 @@ void launch_pyr_down(const PlaneSet& ps, int nplanes, int sh, int sw, int dh, in
 // ====================================================================================================
 // gradients: Sobel k=1 (replicate) then 3x3 sigma 0.5 blur (reflect-101), output interleaved (Ix, Iy)
 // ====================================================================================================
-// Tile of 32 x 8 outputs from a shared-memory tile of I with a 2-pixel halo.  Sobel uses replicated borders, the 3x3
-// blur reflect-101 of the Sobel image; both index maps stay within 2 pixels of the output position, so every tap is a
-// shared-memory read at (global index - tile origin).
+// Tile of 32 x 8 outputs.  (1) I with a 2-pixel halo into shared memory (replicated borders, which is what the clamped Sobel
+// taps read); (2) the Sobel pair (Ix, Iy) ONCE per position of the tile + 1-pixel halo, at the reflect-101 coordinates the
+// 3x3 blur will ask for; (3) + (4) the separable blur, row pass then column pass, both channels of a pair in one packed
+// fp32x2 instruction.  Same taps, same order, same roundings as computing every Sobel value at every use.
 __global__ void __launch_bounds__(256)
 k_gradient(const float* __restrict__ I, float2* __restrict__ G, int h, int w) {
     PF_GAUSS_TABLES
     __shared__ float s_I[12][36 + 1];
+    __shared__ f2p s_S[10][34];
+    __shared__ f2p s_R[10][32];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
     {
@@ -196,31 +199,35 @@ k_gradient(const float* __restrict__ I, float2* __restrict__ G, int h, int w) {
         }
     }
     __syncthreads();
+    // local (shared-memory) coordinates of global column c / row r: c - (x0 - 2), r - (y0 - 2)
+    const int ox = x0 - 2, oy = y0 - 2;
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+        const int ly = ty + 8 * ry;
+        if (ly < 10) {
+            const int Y = reflect101(min(y0 - 1 + ly, h), h) - oy;       // rows past h are only used by outputs past the image
+#pragma unroll
+            for (int rx = 0; rx < 2; ++rx) {
+                const int lx = tx + 32 * rx;
+                if (lx < 34) {
+                    const int X = reflect101(min(x0 - 1 + lx, w), w) - ox;
+                    // Sobel k = 1 with BORDER_REPLICATE: the tile holds replicated values outside the image
+                    s_S[ly][lx] = pk(fsub(s_I[Y][X + 1], s_I[Y][X - 1]), fsub(s_I[Y + 1][X], s_I[Y - 1][X]));
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+        const int ly = ty + 8 * ry;
+        if (ly < 10)
+            s_R[ly][tx] = padd(pmuls(s_S[ly][tx + 1], kG3H[0]), pmuls(padd(s_S[ly][tx], s_S[ly][tx + 2]), kG3H[1]));
+    }
+    __syncthreads();
     const int x = x0 + tx, y = y0 + ty;
     if (x >= w || y >= h) return;
-    // local (shared-memory) coordinates of global column c / row r: c - (x0 - 2), r - (y0 - 2).  Positions outside the
-    // image were loaded with replicated values, which is exactly what the clamped Sobel taps read.
-    const int ox = x0 - 2, oy = y0 - 2;
-    const int xs[3] = { reflect101(x - 1, w), x, reflect101(x + 1, w) };
-    float rx[3], ry[3];
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = reflect101(y + dy, h);
-        const int ly = yy - oy, lyp = clampi(yy + 1, 0, h - 1) - oy, lym = clampi(yy - 1, 0, h - 1) - oy;
-        float sx[3], sy[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int xx = xs[k];
-            sx[k] = fsub(s_I[ly][clampi(xx + 1, 0, w - 1) - ox], s_I[ly][clampi(xx - 1, 0, w - 1) - ox]);
-            sy[k] = fsub(s_I[lyp][xx - ox], s_I[lym][xx - ox]);
-        }
-        rx[dy + 1] = fadd(fmul(sx[1], kG3H[0]), fmul(fadd(sx[0], sx[2]), kG3H[1]));
-        ry[dy + 1] = fadd(fmul(sy[1], kG3H[0]), fmul(fadd(sy[0], sy[2]), kG3H[1]));
-    }
-    float2 o;
-    o.x = fadd(fmul(kG3H[0], rx[1]), fmul(kG3H[1], fadd(rx[2], rx[0])));
-    o.y = fadd(fmul(kG3H[0], ry[1]), fmul(kG3H[1], fadd(ry[2], ry[0])));
-    G[y * w + x] = o;
+    G[y * w + x] = upk(padd(pmuls(s_R[ty + 1][tx], kG3H[0]), pmuls(padd(s_R[ty + 2][tx], s_R[ty][tx]), kG3H[1])));
     (void)kG5; (void)kG3O; (void)kG15;
 }
 
