@@ -217,3 +217,40 @@ def test_four_input_single_pass_like_main(orc, engine_search):
     d = np.abs(final.astype(int) - want.astype(int))
     assert d[..., :3].max() <= 1 and d[..., 3].max() == 0
     assert np.array_equal(final[inter["map"] != 150], want[inter["map"] != 150])
+
+
+def _flat_pair(rows, cols, aL, aR, seed=3):
+    rng = np.random.default_rng(seed)
+    L = rng.integers(1, 256, (rows, cols, 4), dtype=np.uint8)
+    R = rng.integers(1, 256, (rows, cols, 4), dtype=np.uint8)
+    L[..., 3] = np.where(aL, 255, 0)
+    R[..., 3] = np.where(aR, 255, 0)
+    return L, R
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["no_overlap", "full_overlap", "left_empty", "both_empty"])
+def test_stitch_prepare_degenerate_canvases(orc, engine_low, case):
+    """no overlap (nothing to smooth), full overlap (countblend finds neither image: blend 0.5, MergedDis = 10*cols, EVERY
+    block is smoothed -- the densest dependency pattern the block wavefront can see), and empty inputs"""
+    import panorama_opticalflow_b200 as pf
+    rows, cols = 440, 260
+    x = np.mgrid[0:rows, 0:cols][1]
+    t, f = np.ones((rows, cols), bool), np.zeros((rows, cols), bool)
+    aL, aR = {"no_overlap": (x < 100, x >= 130), "full_overlap": (t, t), "left_empty": (f, x > 40), "both_empty": (f, f)}[case]
+    L, R = _flat_pair(rows, cols, aL, aR)
+    st = pf.Stitchtools(engine_low)
+    st.prepare(L, R)
+    m, oL, oR = orc.stitch_match_and_mask(L, R)
+    braw, md = orc.stitch_blend_raw(m)
+    assert_bit_equal(st.getMap(), m, "Map")
+    assert_bit_equal(st.getBlendUnsmoothed(), braw, "blend (un-smoothed)")
+    assert_bit_equal(st.MergedDis, md, "MergedDis")
+    assert_bit_equal(st.getBlend(), orc.stitch_blend_smooth(braw, md), "Blend")
+    if case == "full_overlap":
+        assert (md > 1).all() and np.all(braw == 0.5)
+    M = np.zeros((rows, cols, 4), np.uint8)
+    M[m == 150] = 200
+    st.setMergedmiddle(M)
+    st.Gather()
+    assert_bit_equal(st.getFinalResult(), orc.stitch_gather(L, R, M, m), "FinalResult")
