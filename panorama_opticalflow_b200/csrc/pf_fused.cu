@@ -132,7 +132,14 @@ k_median5(const float2* __restrict__ src, float2* __restrict__ dst, const float2
             vx[dy * 5 + dx] = v.x;
             vy[dy * 5 + dx] = v.y;
         }
+#ifndef PF_MEDIAN_S3
+#define PF_MEDIAN_S3 1
+#endif
+#if PF_MEDIAN_S3
+    const float2 m = make_float2(median25_s3(vx), median25_s3(vy));
+#else
     const float2 m = make_float2(median25(vx), median25(vy));
+#endif
     const size_t p = (size_t)y * w + x;
     dst[p] = m;
     if (MODE == MODE_PREP) emit_record(pa, make_err_ctx(pa.G1, w, h), x, y, w, h, m, blurred[p]);

@@ -101,6 +101,28 @@ __device__ __forceinline__ float median25(float v[25]) {
     return v[12];
 }
 
+// The same selection network with its 21 three-element sorts (bubble triples (j,k),(i,k),(i,j) of the list above) done by
+// Blackwell's 3-input min/max: lo = min3, hi = max3, mid = a ^ b ^ c ^ lo ^ hi on the bit patterns (lo and hi are bit copies
+// of two of the inputs, so the XOR leaves exactly the third).  FMNMX, FMNMX3 and the logic ops all issue on the half-rate ALU
+// pipe (tools/microbench_minmax.cu), which bounds the median kernels: 4 ALU operations per sorted triple instead of 6.
+// NaN-free inputs only (the XOR identity needs min3/max3 to return input bit patterns); the callers' flows are finite.
+#define PF_SORT3(a, b, c) { const float x_ = v[a], y_ = v[b], z_ = v[c]; \
+    const float lo_ = fminf(fminf(x_, y_), z_), hi_ = fmaxf(fmaxf(x_, y_), z_); \
+    v[b] = __int_as_float(__float_as_int(x_) ^ __float_as_int(y_) ^ __float_as_int(z_) ^ __float_as_int(lo_) ^ __float_as_int(hi_)); \
+    v[a] = lo_; v[c] = hi_; }
+__device__ __forceinline__ float median25_s3(float v[25]) {
+    PF_CSWAP(0,1) PF_SORT3(2,3,4) PF_SORT3(5,6,7) PF_SORT3(8,9,10) PF_SORT3(11,12,13) PF_SORT3(14,15,16)
+    PF_SORT3(17,18,19) PF_SORT3(20,21,22) PF_CSWAP(23,24) PF_CSWAP(2,5) PF_SORT3(0,3,6) PF_SORT3(1,4,7)
+    PF_SORT3(8,11,14) PF_SORT3(9,12,15) PF_SORT3(10,13,16) PF_SORT3(17,20,23) PF_SORT3(18,21,24) PF_CSWAP(19,22)
+    PF_CSWAP(8,17) PF_SORT3(0,9,18) PF_SORT3(1,10,19) PF_SORT3(2,11,20) PF_SORT3(3,12,21) PF_SORT3(4,13,22)
+    PF_SORT3(5,14,23) PF_SORT3(6,15,24) PF_CSWAP(7,16) PF_CSWAP(7,19) PF_CSWAP(13,21) PF_CSWAP(15,23) PF_CSWAP(7,13)
+    PF_CSWAP(7,15) PF_CSWAP(1,9) PF_CSWAP(3,11) PF_CSWAP(5,17) PF_CSWAP(11,17) PF_CSWAP(9,17) PF_CSWAP(4,10)
+    PF_CSWAP(6,12) PF_CSWAP(7,14) PF_CSWAP(4,6) PF_CSWAP(4,7) PF_CSWAP(12,14) PF_CSWAP(10,14) PF_CSWAP(6,7)
+    PF_CSWAP(10,12) PF_CSWAP(6,10) PF_CSWAP(6,17) PF_CSWAP(12,17) PF_CSWAP(7,17) PF_CSWAP(7,10) PF_CSWAP(12,18)
+    PF_CSWAP(7,12) PF_CSWAP(10,18) PF_SORT3(10,12,20)
+    return v[12];
+}
+
 // ---- the PixFlow error function, CPU/PixFlow.hpp:407-456 -------------------------------------------
 // PixFlow presets (CPU/PixFlow.hpp:461-497): both presets share these values
 #define PF_SMOOTHNESS_COEF 0.001f

@@ -92,6 +92,35 @@ def test_median_network_selects_the_median():
     assert np.array_equal(v[:, 12], want)
 
 
+def test_median_network_with_three_element_sorts():
+    """median25_s3: the same network with its bubble triples replaced by 3-input sorts (min3 / max3 / xor) -- must select the
+    median as well, and must be the 99-comparator network regrouped (every triple expands to (j,k),(i,k),(i,j))."""
+    txt = open(os.path.join(ROOT, "panorama_opticalflow_b200", "csrc", "pf_math.cuh")).read()
+    base = txt[txt.index("float median25("):txt.index("return v[12]")]
+    net = [(int(a), int(b)) for a, b in re.findall(r"PF_CSWAP\((\d+),(\d+)\)", base)]
+    body = txt[txt.index("float median25_s3"):]
+    body = body[:body.index("return v[12]")]
+    ops = re.findall(r"PF_(CSWAP|SORT3)\(([\d,]+)\)", body)
+    expanded = []
+    for kind, args in ops:
+        idx = [int(t) for t in args.split(",")]
+        if kind == "CSWAP":
+            expanded.append((idx[0], idx[1]))
+        else:
+            i, j, k = idx
+            assert i < j < k
+            expanded += [(j, k), (i, k), (i, j)]
+    assert expanded == net and sum(1 for k, _ in ops if k == "SORT3") == 22
+    rng = np.random.default_rng(1)
+    v = rng.integers(0, 2, (100000, 25)).astype(np.float32)
+    v = np.concatenate([v, rng.standard_normal((50000, 25)).astype(np.float32), np.tril(np.ones((25, 25), np.float32))])
+    want = np.sort(v, axis=1)[:, 12]
+    for kind, args in ops:
+        idx = [int(t) for t in args.split(",")]
+        v[:, idx] = np.sort(v[:, idx], axis=1)
+    assert np.array_equal(v[:, 12], want)
+
+
 def test_pyramid_plan_matches_survey(orc):
     # SURVEY.md section 8: config 2 through prepare -> level-0 1100x2000, 37 levels, coarsest 25x45
     rows, cols = 4000, 2000
