@@ -269,25 +269,20 @@ k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, float2* __restr
     int xs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) xs[k] = clampi(sx - 1 + k, 0, sw - 1);
-    float rx[4], ry[4];
+    // both channels of a flow vector in one packed fp32x2 instruction per tap (pf_math.cuh)
+    f2p r[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float2* S = src + clampi(sy - 1 + k, 0, sh - 1) * sw;
-        const float2 v0 = S[xs[0]], v1 = S[xs[1]], v2 = S[xs[2]], v3 = S[xs[3]];
-        rx[k] = fadd(fadd(fadd(fmul(v0.x, ca[0]), fmul(v1.x, ca[1])), fmul(v2.x, ca[2])), fmul(v3.x, ca[3]));
-        ry[k] = fadd(fadd(fadd(fmul(v0.y, ca[0]), fmul(v1.y, ca[1])), fmul(v2.y, ca[2])), fmul(v3.y, ca[3]));
+        const f2p* S = reinterpret_cast<const f2p*>(src + clampi(sy - 1 + k, 0, sh - 1) * sw);
+        r[k] = padd(padd(padd(pmuls(S[xs[0]], ca[0]), pmuls(S[xs[1]], ca[1])), pmuls(S[xs[2]], ca[2])), pmuls(S[xs[3]], ca[3]));
     }
-    // vertical pass: right-to-left for the first n - n%4 floats of the row, left-to-right for the tail
+    // vertical pass: right-to-left for the first n - n%4 floats of the row, left-to-right for the tail (n = 2*dw is even and
+    // n - n%4 a multiple of 4, so both floats of a pixel fall on the same side)
     const int n = dw * 2, nv = n - n % 4;
-    float ox, oy;
-    if (2 * x < nv) {
-        ox = fadd(fadd(fadd(fmul(rx[3], cb[3]), fmul(rx[2], cb[2])), fmul(rx[1], cb[1])), fmul(rx[0], cb[0]));
-        oy = fadd(fadd(fadd(fmul(ry[3], cb[3]), fmul(ry[2], cb[2])), fmul(ry[1], cb[1])), fmul(ry[0], cb[0]));
-    } else {
-        ox = fadd(fadd(fadd(fmul(rx[0], cb[0]), fmul(rx[1], cb[1])), fmul(rx[2], cb[2])), fmul(rx[3], cb[3]));
-        oy = fadd(fadd(fadd(fmul(ry[0], cb[0]), fmul(ry[1], cb[1])), fmul(ry[2], cb[2])), fmul(ry[3], cb[3]));
-    }
-    dst[y * dw + x] = make_float2(fmul(ox, PF_INV_PYR), fmul(oy, PF_INV_PYR));
+    f2p o;
+    if (2 * x < nv) o = padd(padd(padd(pmuls(r[3], cb[3]), pmuls(r[2], cb[2])), pmuls(r[1], cb[1])), pmuls(r[0], cb[0]));
+    else            o = padd(padd(padd(pmuls(r[0], cb[0]), pmuls(r[1], cb[1])), pmuls(r[2], cb[2])), pmuls(r[3], cb[3]));
+    dst[y * dw + x] = upk(pmuls(o, PF_INV_PYR));
 }
 
 void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int dh, int dw, cudaStream_t st) {
@@ -311,8 +306,8 @@ k_tail(const float2* __restrict__ src, int sh, int sw, int rows, int pcols, int 
     __shared__ float s_xf[34];
     __shared__ int s_y0[10], s_y1[10];
     __shared__ float s_fy[10];
-    __shared__ float2 s_up[10][34];
-    __shared__ float2 s_rb[10][32];
+    __shared__ f2p s_up[10][34];
+    __shared__ f2p s_rb[10][32];
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
     const int xo0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
     if (tid < 34) {                       // columns xo0-1 .. xo0+32 of the crop = padded columns (+pad), reflected
@@ -330,37 +325,31 @@ k_tail(const float2* __restrict__ src, int sh, int sw, int rows, int pcols, int 
         s_fy[k] = fy;
     }
     __syncthreads();
+    const f2p* srcp = reinterpret_cast<const f2p*>(src);
     for (int e = tid; e < 10 * 34; e += 256) {
         const int ly = e / 34, lx = e - ly * 34;
-        const float2* S0 = src + s_y0[ly] * sw;
-        const float2* S1 = src + s_y1[ly] * sw;
+        const f2p* S0 = srcp + s_y0[ly] * sw;
+        const f2p* S1 = srcp + s_y1[ly] * sw;
         const int s = s_xs[lx];
         const float b1 = s_fy[ly], b0 = fsub(1.0f, b1);
-        float2 r0, r1;
+        f2p r0, r1;
         if (s >= sw - 1) { r0 = S0[s]; r1 = S1[s]; }
         else {
             const float f = s_xf[lx], g = fsub(1.0f, f);
-            const float2 a0 = S0[s], a1 = S0[s + 1], c0 = S1[s], c1 = S1[s + 1];
-            r0.x = fadd(fmul(a0.x, g), fmul(a1.x, f)); r0.y = fadd(fmul(a0.y, g), fmul(a1.y, f));
-            r1.x = fadd(fmul(c0.x, g), fmul(c1.x, f)); r1.y = fadd(fmul(c0.y, g), fmul(c1.y, f));
+            r0 = padd(pmuls(S0[s], g), pmuls(S0[s + 1], f));
+            r1 = padd(pmuls(S1[s], g), pmuls(S1[s + 1], f));
         }
-        s_up[ly][lx] = make_float2(fmul(fadd(fmul(r0.x, b0), fmul(r1.x, b1)), 2.0f),      // flow *= 1/downscaleFactor
-                                   fmul(fadd(fmul(r0.y, b0), fmul(r1.y, b1)), 2.0f));
+        s_up[ly][lx] = pmuls(padd(pmuls(r0, b0), pmuls(r1, b1)), 2.0f);      // flow *= 1/downscaleFactor
     }
     __syncthreads();
     for (int e = tid; e < 10 * 32; e += 256) {      // row pass of the 3x3 blur
         const int ly = e >> 5, lx = e & 31;
-        const float2 l = s_up[ly][lx], c = s_up[ly][lx + 1], r = s_up[ly][lx + 2];
-        s_rb[ly][lx] = make_float2(fadd(fmul(c.x, kG3O[0]), fmul(fadd(l.x, r.x), kG3O[1])),
-                                   fadd(fmul(c.y, kG3O[0]), fmul(fadd(l.y, r.y), kG3O[1])));
+        s_rb[ly][lx] = padd(pmuls(s_up[ly][lx + 1], kG3O[0]), pmuls(padd(s_up[ly][lx], s_up[ly][lx + 2]), kG3O[1]));
     }
     __syncthreads();
     const int xo = xo0 + tx, y = y0 + ty;
     if (xo >= cols || y >= rows) return;
-    const float2 u = s_rb[ty][tx], c = s_rb[ty + 1][tx], d = s_rb[ty + 2][tx];
-    float2 o;
-    o.x = fadd(fmul(kG3O[0], c.x), fmul(kG3O[1], fadd(d.x, u.x)));
-    o.y = fadd(fmul(kG3O[0], c.y), fmul(kG3O[1], fadd(d.y, u.y)));
+    const float2 o = upk(padd(pmuls(s_rb[ty + 1][tx], kG3O[0]), pmuls(padd(s_rb[ty + 2][tx], s_rb[ty][tx]), kG3O[1])));
     *reinterpret_cast<float2*>(reinterpret_cast<char*>(out) + (size_t)y * out_stride + (size_t)xo * sizeof(float2)) = o;
     (void)kG5; (void)kG3H; (void)kG15;
 }
