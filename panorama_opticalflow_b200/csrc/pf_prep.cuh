@@ -40,14 +40,6 @@ __device__ __forceinline__ BilCell bil_cell_rm(const ErrCtx& c, float x, float y
 // (fp32x2, pf_math.cuh)
 struct BilCoef { f2p f00, a2, a3, a4; };
 
-__device__ __forceinline__ BilCoef make_coef(f2p F00, f2p F10, f2p F01, f2p F11) {
-    BilCoef t;
-    t.f00 = F00;
-    t.a2 = psub(F10, F00); t.a3 = psub(F01, F00);
-    t.a4 = psub(psub(padd(F00, F11), F10), F01);
-    return t;
-}
-
 __device__ __forceinline__ BilCoef load_coef_rm(const ErrCtx& c, int x0, int y0) {
     const float2* p = c.G1 + (size_t)y0 * c.w + x0;
     const f2p F00 = pk(__ldg(p)), F10 = pk(__ldg(p + 1)), F01 = pk(__ldg(p + c.w)), F11 = pk(__ldg(p + c.w + 1));
@@ -105,18 +97,9 @@ __device__ __forceinline__ void emit_record(const PrepArgs& a, const ErrCtx& c, 
         const BilCell c0 = bil_cell_rm(c, fadd(xf, f.x), fadd(yf, f.y));
         const BilCell c1 = bil_cell_rm(c, fadd(xf, fx1), fadd(yf, fy1));
         const BilCell c2 = bil_cell_rm(c, fadd(xf, fx2), fadd(yf, fy2));
-        // A probe that leaves the base cell moves exactly one cell right (x probe) or down (y probe), and many pixels sit within
-        // eps of a cell boundary: the 4 extra texels are fetched with the 4 base ones and picked with selects (no divergent
-        // re-gather).  Indices past the plane (last cells only, where no crossing can happen) are clamped.
-        const int i00 = c0.y0 * c.w + c0.x0, last = c.w * c.h - 1;
-        const f2p F00 = pk(__ldg(c.G1 + i00)), F10 = pk(__ldg(c.G1 + i00 + 1));
-        const f2p F01 = pk(__ldg(c.G1 + i00 + c.w)), F11 = pk(__ldg(c.G1 + i00 + c.w + 1));
-        const f2p X0 = pk(__ldg(c.G1 + min(i00 + 2, last))), X1 = pk(__ldg(c.G1 + min(i00 + c.w + 2, last)));
-        const f2p Y0 = pk(__ldg(c.G1 + min(i00 + 2 * c.w, last))), Y1 = pk(__ldg(c.G1 + min(i00 + 2 * c.w + 1, last)));
-        const bool cx = c1.x0 != c0.x0, cy = c2.y0 != c0.y0;
-        const BilCoef t0 = make_coef(F00, F10, F01, F11);
-        const BilCoef t1 = make_coef(cx ? F10 : F00, cx ? X0 : F10, cx ? F11 : F01, cx ? X1 : F11);
-        const BilCoef t2 = make_coef(cy ? F01 : F00, cy ? F11 : F10, cy ? Y0 : F01, cy ? Y1 : F11);
+        // every probe gathers its own bilinear cell (no divergent re-gather when a probe crosses a cell boundary, which is common:
+        // gradient descent parks many pixels within eps of one)
+        const BilCoef t0 = load_coef_rm(c, c0.x0, c0.y0), t1 = load_coef_rm(c, c1.x0, c1.y0), t2 = load_coef_rm(c, c2.x0, c2.y0);
         const f2p g1a = bil_interp(t0, c0.xR, c0.yR), g1b = bil_interp(t1, c1.xR, c1.yR), g1c = bil_interp(t2, c2.xR, c2.yR);
         const float rcp_w = __frcp_rn(c.fw), rcp_eps = __frcp_rn(PF_GRAD_EPS);
         unsigned tiny = 0xffffffffu;

@@ -295,10 +295,10 @@ struct SkewCoef { f2p f00, a2, a3, a4; };
 
 template <int POSX>
 __device__ __forceinline__ SkewCoef skew_gather(const SweepConst& k, int gi) {
-    const float2* p00 = k.G1s + gi;
-    const float2* p1 = p00 + k.pitch;            // anti-diagonal +1: (x0,y0+1) and (x0+1,y0) are adjacent
-    const float2* p2 = p1 + k.pitch;             // anti-diagonal +2
-    const f2p F00 = pk(__ldg(p00)), F10 = pk(__ldg(p1 + (POSX ? 1 : 0))), F01 = pk(__ldg(p1 + (POSX ? 0 : 1))), F11 = pk(__ldg(p2 + 1));
+    const int i1 = gi + k.pitch;                 // anti-diagonal +1: (x0,y0+1) and (x0+1,y0) are adjacent
+    const int i2 = i1 + k.pitch;                 // anti-diagonal +2
+    const f2p F00 = pk(__ldg(k.G1s + gi)), F10 = pk(__ldg(k.G1s + i1 + (POSX ? 1 : 0))), F01 = pk(__ldg(k.G1s + i1 + (POSX ? 0 : 1)));
+    const f2p F11 = pk(__ldg(k.G1s + i2 + 1));
     SkewCoef c;
     c.f00 = F00;
     c.a2 = psub(F10, F00); c.a3 = psub(F01, F00);
@@ -313,23 +313,11 @@ __device__ __forceinline__ float err_from_taps(const SweepConst& k, const SkewCo
     return err_tail<SLOW>(k, G1, g0, bl, fx, fy, tiny, true);
 }
 
-__device__ __forceinline__ SkewCoef skew_coef(f2p F00, f2p F10, f2p F01, f2p F11) {
-    SkewCoef c;
-    c.f00 = F00;
-    c.a2 = psub(F10, F00); c.a3 = psub(F01, F00);
-    c.a4 = psub(psub(padd(F00, F11), F10), F01);
-    return c;
-}
-__device__ __forceinline__ f2p psel(bool p, f2p a, f2p b) { return p ? a : b; }
-
-// The three probes f, f+(eps,0), f+(0,eps) of ONE candidate on one lane.  A probe that leaves the base bilinear cell can only
-// move ONE cell to the right (x probe) or down (y probe) -- gradient descent on the piecewise-bilinear error parks many pixels
-// within eps of a cell boundary, so this happens in most warp-steps (profiles/r1_sweep_v8_ncu.md).  The 4 texels such a probe
-// would additionally need are therefore fetched together with the 4 base texels, in ONE round of loads, and each lane picks
-// its probes' taps with selects: no vote, no branch and no second dependent gather on the step's critical path.
-#ifndef PF_SWEEP_GATHER8
-#define PF_SWEEP_GATHER8 1
-#endif
+// The three probes f, f+(eps,0), f+(0,eps) of ONE candidate on one lane.  Gradient descent on the piecewise-bilinear error
+// parks many pixels within eps of a bilinear-cell boundary, so in most warp-steps some probe falls into the neighbouring
+// cell (73 % in profiles/r1_sweep_v8_ncu.md).  Every probe therefore gathers its own cell unconditionally: 12 loads issued
+// together -- almost always the same one or two L1 lines -- instead of 4 loads, a warp vote, a branch and a second, dependent
+// gather on the step's critical path.
 template <int POSX, bool SLOW>
 __device__ __forceinline__ void eval_err3(const SweepConst& k, float xf, float yf, float2 g0, float2 bl, float2 cand,
                                           float v[3], unsigned& tiny) {
@@ -338,38 +326,12 @@ __device__ __forceinline__ void eval_err3(const SweepConst& k, float xf, float y
     const SkewCell c0 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy0));
     const SkewCell c1 = skew_cell<POSX>(k, fadd(xf, fx1), fadd(yf, fy0));
     const SkewCell c2 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy2));
-#if PF_SWEEP_GATHER8
-    // element indices in 32 bits, one independent 64-bit address per load (no pointer-increment carry chains on the critical path)
-    const int i1 = c0.gi + k.pitch;              // anti-diagonal +1: (x0,y0+1) and (x0+1,y0) are adjacent
-    const int i2 = i1 + k.pitch;                 // +2: (x0,y0+2), (x0+1,y0+1), (x0+2,y0)
-    const int i3 = i2 + k.pitch;                 // +3: (x0+1,y0+2), (x0+2,y0+1)
-    const f2p F00 = pk(__ldg(k.G1s + c0.gi)), F10 = pk(__ldg(k.G1s + i1 + (POSX ? 1 : 0))), F01 = pk(__ldg(k.G1s + i1 + (POSX ? 0 : 1)));
-    const f2p F11 = pk(__ldg(k.G1s + i2 + 1));
-    // the extra texels of the last cells may lie past the array: clamped (their values are unused there)
-    const f2p X0 = pk(__ldg(k.G1s + min(i2 + (POSX ? 2 : 0), k.g1s_last))), Y0 = pk(__ldg(k.G1s + min(i2 + (POSX ? 0 : 2), k.g1s_last)));
-    const f2p X1 = pk(__ldg(k.G1s + min(i3 + (POSX ? 2 : 1), k.g1s_last))), Y1 = pk(__ldg(k.G1s + min(i3 + (POSX ? 1 : 2), k.g1s_last)));
+    const SkewCoef t0 = skew_gather<POSX>(k, c0.gi), t1 = skew_gather<POSX>(k, c1.gi), t2 = skew_gather<POSX>(k, c2.gi);
     {   // warm L1 with the anti-diagonal the gather reaches a few steps from now (asynchronous copy into a scratch slot)
         int pi = c0.gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
         pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
         cp_async16(k.touch, k.G1s + pi);
     }
-    const bool cx = c1.gi != c0.gi, cy = c2.gi != c0.gi;
-    const SkewCoef t0 = skew_coef(F00, F10, F01, F11);
-    const SkewCoef t1 = skew_coef(psel(cx, F10, F00), psel(cx, X0, F10), psel(cx, F11, F01), psel(cx, X1, F11));
-    const SkewCoef t2 = skew_coef(psel(cy, F01, F00), psel(cy, F11, F10), psel(cy, Y0, F01), psel(cy, Y1, F11));
-#else
-    const SkewCoef t0 = skew_gather<POSX>(k, c0.gi);
-    {   // warm L1 with the anti-diagonal the gather reaches a few steps from now (asynchronous copy into a scratch slot)
-        int pi = c0.gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
-        pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
-        cp_async16(k.touch, k.G1s + pi);
-    }
-    SkewCoef t1 = t0, t2 = t0;
-    if (__any_sync(0xffffffffu, c1.gi != c0.gi || c2.gi != c0.gi)) {     // a probe crossed a texel boundary
-        t1 = skew_gather<POSX>(k, c1.gi);
-        t2 = skew_gather<POSX>(k, c2.gi);
-    }
-#endif
     v[0] = err_from_taps<SLOW>(k, t0, c0.xR, c0.yR, g0, bl, fx0, fy0, tiny);
     v[1] = err_from_taps<SLOW>(k, t1, c1.xR, c1.yR, g0, bl, fx1, fy0, tiny);
     v[2] = err_from_taps<SLOW>(k, t2, c2.xR, c2.yR, g0, bl, fx0, fy2, tiny);
@@ -390,8 +352,7 @@ __device__ __forceinline__ void eval_err2(const SweepConst& k, float xf, float y
         pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
         cp_async16(k.touch, k.G1s + pi);
     }
-    SkewCoef t1 = t0;
-    if (__any_sync(0xffffffffu, c1.gi != c0.gi)) t1 = skew_gather<POSX>(k, c1.gi);     // the probe crossed a texel boundary
+    const SkewCoef t1 = skew_gather<POSX>(k, c1.gi);
     v[0] = err_from_taps<SLOW>(k, t0, c0.xR, c0.yR, g0, bl, fxa, fya, tiny);
     v[1] = err_from_taps<SLOW>(k, t1, c1.xR, c1.yR, g0, bl, fxb, fyb, tiny);
 }
