@@ -321,7 +321,9 @@ __device__ __forceinline__ float err_from_taps(const SweepConst& k, const SkewCo
 template <int POSX, bool SLOW>
 __device__ __forceinline__ void eval_err3(const SweepConst& k, float xf, float yf, float2 g0, float2 bl, float2 cand,
                                           float v[3], unsigned& tiny) {
-    const float fx0 = fadd(cand.x, 0.0f), fy0 = fadd(cand.y, 0.0f);
+    // flow + Point2f(eps, 0) / (0, eps) of the reference add +0 to the other component; a -0 component becomes +0 there, which
+    // changes nothing in errorFunction (x + (-0) == x + 0, |-0| == 0, b - (-0) == b - 0), so the candidate is used as it is
+    const float fx0 = cand.x, fy0 = cand.y;
     const float fx1 = fadd(cand.x, PF_GRAD_EPS), fy2 = fadd(cand.y, PF_GRAD_EPS);
     const SkewCell c0 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy0));
     const SkewCell c1 = skew_cell<POSX>(k, fadd(xf, fx1), fadd(yf, fy0));
@@ -379,10 +381,13 @@ __device__ __forceinline__ float2 select_result(float eL, float2 rL, float eU, f
     const float POS_INF = __int_as_float(0x7f800000);
     eL = leftValid ? eL : POS_INF;
     eU = upValid ? eU : POS_INF;
-    float cur = A.x;
+    // decide from the errors alone, pick the vectors last: the candidates' r arrive (shuffles) after their E
+    const bool pL = eL < A.x;
+    const float cur = pL ? eL : A.x;
+    const bool pU = eU < cur;
     float2 out = make_float2(A.y, A.z);
-    if (eL < cur) { out = rL; cur = eL; }
-    if (eU < cur) { out = rU; cur = eU; }
+    out = pL ? rL : out;
+    out = pU ? rU : out;
     return out;
 }
 
@@ -562,8 +567,8 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
                 unsigned t2 = 0xffffffffu;
                 if constexpr (P == 2) {
                     // each lane finishes ITS candidate's gradient step, then the pair swaps {E, r.x, r.y}
+                    const float oe = __shfl_xor_sync(full, v[0], 1);            // E first: it is ready before the gradient step
                     const float2 mine = finish_candidate<SLOW>(k, v, sub != 0 ? up : res, t2);
-                    const float oe = __shfl_xor_sync(full, v[0], 1);
                     const float ox = __shfl_xor_sync(full, mine.x, 1), oy = __shfl_xor_sync(full, mine.y, 1);
                     const float2 other = make_float2(ox, oy);
                     out = select_result(sub == 0 ? v[0] : oe, sub == 0 ? mine : other, sub == 0 ? oe : v[0], sub == 0 ? other : mine,
