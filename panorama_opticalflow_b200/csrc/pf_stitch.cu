@@ -146,7 +146,9 @@ k_stitch_block_blur(BlockBlurArgs a) {
     const int nr = a.step + a.k - 1, an = a.k / 2;
     double* rs = reinterpret_cast<double*>(smem_raw);                     // nr x step
     float* win = reinterpret_cast<float*>(rs + (size_t)nr * a.step);      // nr x nr
-    unsigned char* flag = reinterpret_cast<unsigned char*>(win + (size_t)nr * nr);   // nbx
+    int* gys = reinterpret_cast<int*>(win + (size_t)nr * nr);             // reflect-101 source row / column of each window row / column
+    int* gxs = gys + nr;
+    unsigned char* flag = reinterpret_cast<unsigned char*>(gxs + nr);     // nbx
     __shared__ int s_by;
     const int tid = threadIdx.x, nt = blockDim.x;
     const double scale = 1.0 / (double)(a.k * a.k);
@@ -160,6 +162,7 @@ k_stitch_block_blur(BlockBlurArgs a) {
         const int y = by * a.step;
         const float* mrow = reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.mdis) + (size_t)y * a.strideD);
         for (int bx = tid; bx < a.nbx; bx += nt) flag[bx] = mrow[bx * a.step] > fstep ? 1 : 0;
+        for (int t = tid; t < nr; t += nt) gys[t] = reflect101_dev(y - an + t, a.rows);
         __syncthreads();
         int bx = 0, seen = 0;
         while (bx < a.nbx && !flag[bx]) ++bx;
@@ -173,12 +176,26 @@ k_stitch_block_blur(BlockBlurArgs a) {
                     if (seen < need) __nanosleep(64);
                 }
             __syncthreads();       // no fence: the window is read with ld.cg (L2), never from this SM's L1
-            // ---- window of the current image ----
+            // ---- window of the current image: batches of 8 independent L2 loads per thread, stored to shared memory afterwards
+            // (a load-then-store loop would serialise on the L2 latency, which dominated the per-block time) ----
             const int x = bx * a.step;
-            for (int idx = tid; idx < nr * nr; idx += nt) {
-                const int wy = idx / nr, wx = idx - wy * nr;
-                const int gy = reflect101_dev(y - an + wy, a.rows), gx = reflect101_dev(x - an + wx, a.cols);
-                win[idx] = __ldcg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.blend) + (size_t)gy * a.stride) + gx);
+            for (int t = tid; t < nr; t += nt) gxs[t] = reflect101_dev(x - an + t, a.cols);
+            __syncthreads();
+            for (int base = 0; base < nr * nr; base += nt * 8) {
+                float vv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * nt + tid;
+                    if (idx < nr * nr) {
+                        const int wy = idx / nr, wx = idx - wy * nr;
+                        vv[u] = __ldcg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.blend) + (size_t)gys[wy] * a.stride) + gxs[wx]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * nt + tid;
+                    if (idx < nr * nr) win[idx] = vv[u];
+                }
             }
             __syncthreads();
             for (int r = tid; r < nr; r += nt) box_row_sums(win + r * nr, a.step, a.k, rs + (size_t)r * a.step, 1);
@@ -389,7 +406,7 @@ int stitch_smooth_geometry(int rows, int cols, int* step, int* k1, int* k2, size
     if (st < 1 || *k2 < 1) return 1;                    // the reference cannot run either (endless loop / empty kernel)
     if (*k2 > BOX_KMAX) return 2;
     const int nr = st + *k1 - 1, nbx = (cols - 1) / st;
-    *smem_bytes = (size_t)nr * st * sizeof(double) + (size_t)nr * nr * sizeof(float) + (size_t)nbx + 16;
+    *smem_bytes = (size_t)nr * st * sizeof(double) + (size_t)nr * nr * sizeof(float) + (size_t)2 * nr * sizeof(int) + (size_t)nbx + 16;
     return *smem_bytes > (size_t)200 * 1024 ? 2 : 0;
 }
 
