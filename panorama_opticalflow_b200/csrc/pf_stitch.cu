@@ -52,6 +52,8 @@ k_stitch_blend_raw(const uint8_t* __restrict__ map, size_t strideM, int rows, in
         const double sqrt2 = 1.4142135623730951;                    // sqrt(2) in double, as the CPU path computes it
         for (int i = 0; i < cols / 2; i += step) {
             const float fi = (float)i;
+            // every candidate of this and of all later iterations is at distance >= i: nothing can improve any more
+            if (fi >= minL && fi >= minR) break;
             const double di = __dmul_rn((double)i, sqrt2);
             const float fd = __double2float_rn(di);
             const bool xp = xe + i < ecols, xm = xe - i > 0, yp = y + i < rows, ym = y - i > 0;
