@@ -21,8 +21,12 @@
 //   * the sweep kernel only evaluates the two neighbour candidates -- left (the row's own previous result) and up
 //     (previous result of the row above, one shuffle away) -- speculatively at the three probe offsets (0,0), (eps,0),
 //     (0,eps) each, finishes BOTH candidates' gradient steps and then does the reference's two compares.
-//     P lanes per row (template): P = 2 (default) one candidate per lane, three probes sharing one texel gather;
-//     P = 8 one probe per lane (six shuffles collect the errors); P = 1 both candidates on one lane.
+//     P lanes per row (template): P = 2 (default) one candidate per lane -- its three probes each gather their own
+//     bilinear cell (12 independent loads, almost always the same L1 lines), the lane finishes its candidate's gradient
+//     step and the pair swaps {E, r}; P = 8 one probe per lane (six shuffles collect the errors); P = 4 two probes per
+//     lane; P = 1 both candidates on one lane.
+//   * the (x, y) channel pairs of gradients and flows go through Blackwell's packed fp32x2 pipe (FFMA2 / FADD2,
+//     pf_math.cuh): bit-identical to the scalar operations, half the instructions.
 //   * the step body is branch-free: the IEEE divisions (by eps and by cols, both loop-invariant) and square roots
 //     use exactly-rounded branchless sequences (pf_math.cuh, verified exhaustively on the GPU); a warp-uniform
 //     vote redoes the step with the IEEE intrinsics in the rare case an operand leaves their validity range.
@@ -34,10 +38,10 @@
 //   * persistent CTAs: the grid is only as wide as the wavefront (front + margin); a CTA takes the next row-block
 //     ticket when it finishes one.  Tickets are handed out in row-block order, so the block a CTA waits on is always
 //     being processed or done (no deadlock whatever the residency).  Warps queued behind the front sleep-poll.
-//   * measured (profiles/): the step is bound by the in-order dependent instruction chain of one warp (~1400 cycles
-//     for ~270-450 instructions), not by memory; throughput comes from interleaving independent wavefronts (both
-//     directions, several pairs) on the same schedulers -- < 30 KB of shared memory and < 100 registers per thread
-//     keep several sweep CTAs resident per SM.
+//   * measured (profiles/r1_sweep_v8_ncu.md): the step is bound by the in-order dependent instruction chain of one warp
+//     (~1100 cycles for 360 instructions at P = 2: dependency waits 37 %, issue 33 %, L1 misses of the gather 9 %), not by
+//     memory; throughput comes from interleaving independent wavefronts (both directions, several pairs) on the same
+//     schedulers -- 23 KB of shared memory and 126 registers per thread keep three sweep CTAs resident per SM.
 #include <cstdlib>
 #include <type_traits>
 
