@@ -406,6 +406,82 @@ __device__ __forceinline__ float2 finish_pixel(const SweepConst& k, const float 
     return select_result(e6[0], rL, e6[3], rU, leftValid, upValid, A);
 }
 
+// One step of one lane: evaluate this lane's probes, finish the candidates, select (the body of the wavefront loop).
+// SLOW = false: branch-free exact sequences, tkey / vmax collect what their validity check needs; SLOW = true: IEEE intrinsics.
+template <int POSX, int P, bool SLOW>
+__device__ __forceinline__ float2 step_eval(const SweepConst& k, float xf, float yf, float4 A, float4 B, float2 res, float2 up,
+                                            int i, int j, int sub, int gbase, unsigned& tkey, float& vmax) {
+    typedef SweepGeom<P> G;
+    const unsigned full = 0xffffffffu;
+    const float2 g0 = make_float2(B.x, B.y), bl = make_float2(B.z, B.w);
+    float2 out = make_float2(A.y, A.z);
+    float v[G::NQ];
+    // P = 8: this lane's single probe (lanes 0-2 left candidate, 3-5 up candidate, 6-7 duplicates of 3-4)
+    const bool candUp8 = sub >= 3;
+    const float offx8 = (sub % 3) == 1 ? PF_GRAD_EPS : 0.0f, offy8 = (sub % 3) == 2 ? PF_GRAD_EPS : 0.0f;
+    (void)candUp8; (void)offx8; (void)offy8; (void)gbase;
+    if constexpr (P == 8) {
+        const float2 cand = candUp8 ? up : res;
+        unsigned t1 = 0xffffffffu;
+        v[0] = eval_err<POSX, SLOW>(k, xf, yf, g0, bl, fadd(cand.x, offx8), fadd(cand.y, offy8), t1);
+        tkey = min(tkey, t1);
+    } else if constexpr (P == 4) {
+        eval_err2<POSX, SLOW>(k, xf, yf, g0, bl, sub >= 2 ? up : res, (sub & 1) != 0, v, tkey);
+    } else if constexpr (P == 2) {
+        eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, sub != 0 ? up : res, v, tkey);
+    } else {
+        eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, res, v, tkey);
+        eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, up, v + 3, tkey);
+    }
+#pragma unroll
+    for (int q = 0; q < G::NQ; ++q) {
+        vmax = fmaxf(vmax, fabsf(v[q]));
+        if (!(v[q] == v[q])) vmax = __int_as_float(0x7f800000);      // NaN -> flagged
+    }
+    unsigned t2 = 0xffffffffu;
+    if constexpr (P == 2) {
+        // each lane finishes ITS candidate's gradient step, then the pair swaps {E, r.x, r.y}
+        const float oe = __shfl_xor_sync(full, v[0], 1);            // E first: it is ready before the gradient step
+        const float2 mine = finish_candidate<SLOW>(k, v, sub != 0 ? up : res, t2);
+        const float ox = __shfl_xor_sync(full, mine.x, 1), oy = __shfl_xor_sync(full, mine.y, 1);
+        const float2 other = make_float2(ox, oy);
+        out = select_result(sub == 0 ? v[0] : oe, sub == 0 ? mine : other, sub == 0 ? oe : v[0], sub == 0 ? other : mine,
+                            i > 0, j > 0, A);
+    } else if constexpr (P == 4) {
+        // lanes {0,1} of a row hold the left candidate's {E, E+dx | E+dy}, lanes {2,3} the up candidate's: the even
+        // lane of each pair finishes its candidate, then all four lanes fetch both {E, r.x, r.y}
+        const float edy = __shfl_xor_sync(full, v[0], 1);
+        const float e3[3] = {v[0], v[1], edy};
+        const float2 mine = finish_candidate<SLOW>(k, e3, sub >= 2 ? up : res, t2);
+        t2 = (sub & 1) ? 0xffffffffu : t2;               // the odd lanes' finish is a don't-care
+        const float eL = __shfl_sync(full, v[0], gbase), eU = __shfl_sync(full, v[0], gbase + 2);
+        const float2 rL = make_float2(__shfl_sync(full, mine.x, gbase), __shfl_sync(full, mine.y, gbase));
+        const float2 rU = make_float2(__shfl_sync(full, mine.x, gbase + 2), __shfl_sync(full, mine.y, gbase + 2));
+        out = select_result(eL, rL, eU, rU, i > 0, j > 0, A);
+    } else {
+        // every lane of the row gets the six errors {L, L+dx, L+dy, U, U+dx, U+dy}
+        float e6[6];
+        if (P == 8) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) e6[q] = __shfl_sync(full, v[0], gbase + q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) e6[q] = v[q % G::NQ];
+        }
+        out = finish_pixel<SLOW>(k, e6, res, up, i > 0, j > 0, A, t2);
+    }
+    tkey = min(tkey, t2);
+    return out;
+}
+
+template <int POSX, int P>
+__device__ __noinline__ float2 step_eval_slow(SweepConst k, float xf, float yf, float4 A, float4 B, float2 res, float2 up,
+                                              int i, int j, int sub, int gbase) {
+    unsigned tkey = 0xffffffffu;
+    float vmax = 0.0f;
+    return step_eval<POSX, P, true>(k, xf, yf, A, B, res, up, i, j, sub, gbase, tkey, vmax);
+}
+
 // Shared memory of one sweep CTA.
 template <int P> struct SweepSmem {
     typedef SweepGeom<P> G;
@@ -484,9 +560,6 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
     asm volatile("" : "+r"(w), "+r"(k.pitch), "+r"(k.dstep), "+r"(k.g1s_last));     // keep loop invariants in registers
     asm volatile("" : "+f"(k.wm2), "+f"(k.hm2), "+f"(k.fw), "+f"(k.rcp_w), "+f"(k.rcp_eps));
     const float NEG_INF = __int_as_float(0xff800000);
-    // P = 8: this lane's single probe (lanes 0-2 left candidate, 3-5 up candidate, 6-7 duplicates of 3-4)
-    const bool candUp8 = sub >= 3;
-    const float offx8 = (sub % 3) == 1 ? PF_GRAD_EPS : 0.0f, offy8 = (sub % 3) == 2 ? PF_GRAD_EPS : 0.0f;
     const float yf = (float)y;
     float xf = (float)(DIR > 0 ? -g : w - 1 + g);                  // float(x) of step 0, then +-1 per step (exact)
     float2* flow_row = a.flow + (size_t)y * w;
@@ -544,68 +617,13 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
         const bool active = valid && A.x > NEG_INF;
         float2 out = make_float2(A.y, A.z);
         if (__any_sync(full, active)) {           // warp-uniform: skip fully inactive stretches
-            const float2 g0 = make_float2(B.x, B.y), bl = make_float2(B.z, B.w);
-            float v[G::NQ];
             unsigned tkey = 0xffffffffu;
             float vmax = 0.0f;
-            auto run = [&](auto slow_tag) {
-                constexpr bool SLOW = decltype(slow_tag)::value;
-                if constexpr (P == 8) {
-                    const float2 cand = candUp8 ? up : res;
-                    unsigned t1 = 0xffffffffu;
-                    v[0] = eval_err<POSX, SLOW>(k, xf, yf, g0, bl, fadd(cand.x, offx8), fadd(cand.y, offy8), t1);
-                    tkey = min(tkey, t1);
-                } else if constexpr (P == 4) {
-                    eval_err2<POSX, SLOW>(k, xf, yf, g0, bl, sub >= 2 ? up : res, (sub & 1) != 0, v, tkey);
-                } else if constexpr (P == 2) {
-                    eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, sub != 0 ? up : res, v, tkey);
-                } else {
-                    eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, res, v, tkey);
-                    eval_err3<POSX, SLOW>(k, xf, yf, g0, bl, up, v + 3, tkey);
-                }
-#pragma unroll
-                for (int q = 0; q < G::NQ; ++q) {
-                    vmax = fmaxf(vmax, fabsf(v[q]));
-                    if (!(v[q] == v[q])) vmax = __int_as_float(0x7f800000);      // NaN -> flagged
-                }
-                unsigned t2 = 0xffffffffu;
-                if constexpr (P == 2) {
-                    // each lane finishes ITS candidate's gradient step, then the pair swaps {E, r.x, r.y}
-                    const float oe = __shfl_xor_sync(full, v[0], 1);            // E first: it is ready before the gradient step
-                    const float2 mine = finish_candidate<SLOW>(k, v, sub != 0 ? up : res, t2);
-                    const float ox = __shfl_xor_sync(full, mine.x, 1), oy = __shfl_xor_sync(full, mine.y, 1);
-                    const float2 other = make_float2(ox, oy);
-                    out = select_result(sub == 0 ? v[0] : oe, sub == 0 ? mine : other, sub == 0 ? oe : v[0], sub == 0 ? other : mine,
-                                        i > 0, j > 0, A);
-                } else if constexpr (P == 4) {
-                    // lanes {0,1} of a row hold the left candidate's {E, E+dx | E+dy}, lanes {2,3} the up candidate's: the even
-                    // lane of each pair finishes its candidate, then all four lanes fetch both {E, r.x, r.y}
-                    const float edy = __shfl_xor_sync(full, v[0], 1);
-                    const float e3[3] = {v[0], v[1], edy};
-                    const float2 mine = finish_candidate<SLOW>(k, e3, sub >= 2 ? up : res, t2);
-                    t2 = (sub & 1) ? 0xffffffffu : t2;               // the odd lanes' finish is a don't-care
-                    const float eL = __shfl_sync(full, v[0], gbase), eU = __shfl_sync(full, v[0], gbase + 2);
-                    const float2 rL = make_float2(__shfl_sync(full, mine.x, gbase), __shfl_sync(full, mine.y, gbase));
-                    const float2 rU = make_float2(__shfl_sync(full, mine.x, gbase + 2), __shfl_sync(full, mine.y, gbase + 2));
-                    out = select_result(eL, rL, eU, rU, i > 0, j > 0, A);
-                } else {
-                    // every lane of the row gets the six errors {L, L+dx, L+dy, U, U+dx, U+dy}
-                    float e6[6];
-                    if (P == 8) {
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) e6[q] = __shfl_sync(full, v[0], gbase + q);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) e6[q] = v[q % G::NQ];
-                    }
-                    out = finish_pixel<SLOW>(k, e6, res, up, i > 0, j > 0, A, t2);
-                }
-                tkey = min(tkey, t2);
-            };
-            run(std::false_type());
+            out = step_eval<POSX, P, false>(k, xf, yf, A, B, res, up, i, j, sub, gbase, tkey, vmax);
             // operands left the range of the branch-free sequences (tiny non-zero, or huge / inf / NaN)?
             const bool bad = (tkey < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f);
-            if (__any_sync(full, bad && active)) run(std::true_type());   // rare: redo the step with the IEEE intrinsics
+            // rare: redo the step with the IEEE intrinsics -- out of line, so that the hot loop stays compact in the instruction cache
+            if (__any_sync(full, bad && active)) out = step_eval_slow<POSX, P>(k, xf, yf, A, B, res, up, i, j, sub, gbase);
         }
         res.x = valid ? out.x : res.x;
         res.y = valid ? out.y : res.y;
