@@ -254,3 +254,27 @@ def test_stitch_prepare_degenerate_canvases(orc, engine_low, case):
     st.setMergedmiddle(M)
     st.Gather()
     assert_bit_equal(st.getFinalResult(), orc.stitch_gather(L, R, M, m), "FinalResult")
+
+
+@pytest.mark.gpu
+def test_stitch_prepare_and_gather_full_size(orc, engine_low):
+    """BASELINE config 2's canvas size (4000 x 2000): the stitching oracle is fast enough to check every output bit for bit
+    (30 800 smoothed blocks, search step 10, blur kernels 30 and 10)."""
+    import panorama_opticalflow_b200 as pf
+    rows, cols = 4000, 2000
+    y, x = np.mgrid[0:rows, 0:cols]
+    L, R = _flat_pair(rows, cols, x < 1400 + 40 * np.sin(y / 211.0), x > 600 - 30 * np.cos(y / 173.0), seed=12)
+    st = pf.Stitchtools(engine_low)
+    st.prepare(L, R)
+    m, oL, oR = orc.stitch_match_and_mask(L, R)
+    braw, md = orc.stitch_blend_raw(m)
+    assert_bit_equal(st.getMap(), m, "Map")
+    assert_bit_equal(st.getOverlappedL(), oL, "OverlappedL")
+    assert_bit_equal(st.getBlendUnsmoothed(), braw, "blend (un-smoothed)")
+    assert_bit_equal(st.MergedDis, md, "MergedDis")
+    assert (md[:rows - 10:10, :cols - 10:10] > 10).sum() > 20000
+    assert_bit_equal(st.getBlend(), orc.stitch_blend_smooth(braw, md), "Blend")
+    M = _merged_with_holes(m, 4)
+    st.setMergedmiddle(M)
+    st.Gather()
+    assert_bit_equal(st.getFinalResult(), orc.stitch_gather(L, R, M, m), "FinalResult")
