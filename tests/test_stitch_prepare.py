@@ -278,3 +278,34 @@ def test_stitch_prepare_and_gather_full_size(orc, engine_low):
     st.setMergedmiddle(M)
     st.Gather()
     assert_bit_equal(st.getFinalResult(), orc.stitch_gather(L, R, M, m), "FinalResult")
+
+
+@pytest.mark.gpu
+def test_stitch_iteration_full_size_composition(orc, engine_search):
+    """One whole iteration (CPU/main.cpp:72-95) on a 4000 x 2000 canvas.  The CPU flow oracle is too slow at this size, so
+    the fused call is checked through its composition: Map and Blend bit for bit against the oracle, Mergedmiddle against
+    the oracle's combineNovelViews fed with the flows the step-by-step API returns for the same inputs (1 LSB), FinalResult
+    bit for bit against the oracle's Gather of that Mergedmiddle; and the call is deterministic."""
+    import panorama_opticalflow_b200 as pf
+    from panorama_opticalflow_b200 import synth
+    rows, cols = 4000, 2000
+    L, R = synth.make_pair(rows, cols, seed=2, amplitude=30.0, sparse=False)
+    x = np.mgrid[0:rows, 0:cols][1]
+    L[..., 3] = np.where(x < 1400, 255, 0)
+    R[..., 3] = np.where(x > 600, 255, 0)
+    L[L[..., 3] == 0] = 0
+    R[R[..., 3] == 0] = 0
+    final, extra = pf.stitch_iteration(engine_search, L, R, want_intermediates=True)
+    final2 = pf.stitch_iteration(engine_search, L, R)
+    assert_bit_equal(final2, final, "second run")
+    m, oL, oR = orc.stitch_match_and_mask(L, R)
+    braw, md = orc.stitch_blend_raw(m)
+    blend = orc.stitch_blend_smooth(braw, md)
+    assert_bit_equal(extra["Map"], m, "Map")
+    assert_bit_equal(extra["Blend"], blend, "Blend")
+    fLR, fRL = engine_search.prepareBidirectional(oL, oR)
+    want_merged = orc.combine_novel_views(oL, oR, fLR, fRL, blend)
+    d = np.abs(extra["Mergedmiddle"].astype(int) - want_merged.astype(int))
+    assert d[..., :3].max() <= 1 and d[..., 3].max() == 0
+    assert_bit_equal(final, orc.stitch_gather(L, R, extra["Mergedmiddle"], m), "FinalResult")
+    assert (final[..., 3] > 0).mean() > 0.99
