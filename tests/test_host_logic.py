@@ -121,6 +121,36 @@ def test_median_network_with_three_element_sorts():
     assert np.array_equal(v[:, 12], want)
 
 
+def test_median_networks_exhaustively_by_the_zero_one_principle():
+    """A comparator network selects the median of every input iff it does so for all 2^25 zero-one inputs.  Bit-parallel:
+    each wire is a 2^25-bit vector (input number i has bit w of i on wire w), min = AND, max = OR, and the middle of a
+    3-input sort a ^ b ^ c ^ lo ^ hi is the majority.  Checks both median25 (2-input) and median25_s3 (3-input sorts)."""
+    txt = open(os.path.join(ROOT, "panorama_opticalflow_b200", "csrc", "pf_math.cuh")).read()
+    n = 1 << 25
+    idx = np.arange(n, dtype=np.uint32)
+    wires0 = [np.packbits(((idx >> w) & 1).astype(np.uint8)) for w in range(25)]
+    count = np.zeros(n, np.uint8)
+    for w in range(25):
+        count += ((idx >> w) & 1).astype(np.uint8)
+    want = np.packbits((count >= 13).astype(np.uint8))      # the 13th smallest of 25 zero-one values is 1 iff >= 13 ones
+    del idx, count
+    for name in ("float median25(", "float median25_s3("):
+        body = txt[txt.index(name):]
+        body = body[:body.index("return v[12]")]
+        v = [w.copy() for w in wires0]
+        for kind, args in re.findall(r"PF_(CSWAP|SORT3)\(([\d,]+)\)", body):
+            t = [int(q) for q in args.split(",")]
+            if kind == "CSWAP":
+                a, b = t
+                v[a], v[b] = v[a] & v[b], v[a] | v[b]
+            else:
+                a, b, c = t
+                lo, hi = v[a] & v[b] & v[c], v[a] | v[b] | v[c]
+                v[b] = v[a] ^ v[b] ^ v[c] ^ lo ^ hi
+                v[a], v[c] = lo, hi
+        assert np.array_equal(v[12], want), name
+
+
 def test_pyramid_plan_matches_survey(orc):
     # SURVEY.md section 8: config 2 through prepare -> level-0 1100x2000, 37 levels, coarsest 25x45
     rows, cols = 4000, 2000
