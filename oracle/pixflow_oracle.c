@@ -2,8 +2,10 @@
  * pixflow_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * CPU restatement (plain C, fp32, no FMA contraction) of the reference hot path of
- * MungoMeng/Panorama-OpticalFlow: the PixFlow flow engine (CPU/PixFlow.hpp) and the
- * novel-view prepare/combine functions (CPU/OpticalFlow.cpp).  Only tests/,
+ * MungoMeng/Panorama-OpticalFlow: the PixFlow flow engine (CPU/PixFlow.hpp), the
+ * novel-view prepare/combine functions (CPU/OpticalFlow.cpp) and -- sections C and D -- the
+ * stitching step around them (CPU/StitchTool.cpp: prepare, MatchImages, GenerateBlend with
+ * countblend and its cv::blur smoothing, Gather; CPU_4Input/main.cpp:64-79).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
  *
  * Parity status: the reference cannot be compiled in this image (needs OpenCV C++, glog, gflags;
@@ -14,7 +16,11 @@
  *       reference calls (README.md:34 pins "OpenCV-3.20");
  *   (2) the loops (section B) are transcriptions of the reference loops, each function citing
  *       the file:line it follows, and the whole pipeline is cross-checked against a second,
- *       independent composition of cv2 calls (oracle/cv2_oracle.py).
+ *       independent composition of cv2 calls (oracle/cv2_oracle.py);
+ *   (3) the box filter of the blend smoothing (section D) is checked bit-for-bit against cv2.blur on
+ *       data whose double-precision running sums are inexact, and the whole smoothing against a
+ *       crop-based cv2 composition (tests/test_stitch_smooth_gather_cpu.py).
+ * Parity against the reference's own binary stays UNPINNED (it cannot be built, it has no tests).
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile).  Never -march=native.
  * All images are row-major and contiguous.  "c2" = 2 interleaved channels.
