@@ -71,6 +71,23 @@ PF_API int pf_prepare_bidirectional_batch(pf_engine* engine, int n,
                                           void* const* flows_l_to_r, size_t stride_lr,
                                           void* const* flows_r_to_l, size_t stride_rl);
 
+/* Asynchronous form of the batch call ("optional async/stream + batch variants for replicas";
+ * the reference itself is synchronous, CPU/OpticalFlow.cpp:128-141).  Enqueues the uploads (one H2D stream, pair order), the
+ * 2n flow computations and the downloads (one D2H stream) and returns at once; the outputs are complete after
+ * pf_wait(engine, slot).  slot is 0 or 1: the two slots own disjoint sets of workspaces, so a caller that alternates slots
+ *     async(slot 0, batch k);  async(slot 1, batch k+1);  wait(slot 0);  async(slot 0, batch k+2);  wait(slot 1); ...
+ * overlaps the download of batch k and the upload of batch k+2 with the compute of batch k+1.  Re-using a slot whose batch
+ * has not been waited for waits for it first.  Input and output buffers must stay valid and untouched until pf_wait returns;
+ * host buffers should be pinned (pf_host_alloc) or the copies degrade to synchronous ones.  The synchronous calls above use
+ * slot 0 and wait for whatever is pending on it. */
+PF_API int pf_prepare_bidirectional_batch_async(pf_engine* engine, int slot, int n,
+                                                const void* const* images_l, size_t stride_l,
+                                                const void* const* images_r, size_t stride_r,
+                                                int rows, int cols,
+                                                void* const* flows_l_to_r, size_t stride_lr,
+                                                void* const* flows_r_to_l, size_t stride_rl);
+PF_API int pf_wait(pf_engine* engine, int slot);
+
 /* Replaces NovelViewUtil::combineNovelViews(imageL, imageR, flowLtoR, flowRtoL, blend),
  * CPU/OpticalFlow.cpp:30-92 (generateNovelViewPoint :9-28 inlined).  out_bgra: rows x cols BGRA8. */
 PF_API int pf_combine_novel_views(pf_engine* engine,

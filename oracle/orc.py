@@ -214,7 +214,10 @@ def compute_flow(i0, i1, max_percentage, hint, trace=None):
     return flow
 
 
-def prepare_bidirectional(L, R, max_percentage):
+def prepare_bidirectional(L, R, max_percentage, threads=1):
+    """NovelViewGeneratorAsymmetricFlow::prepare.  threads=2 runs the two (independent) directions on two host threads --
+    identical results; process-wide setting, so do not mix values across concurrent callers."""
+    lib().orc_set_prepare_threads(int(threads))
     L, pl = _u(L)
     R, pr = _u(R)
     rows, cols, _ = L.shape
@@ -297,13 +300,22 @@ def stitch_gather(imageL, imageR, merged, map_u8):
     return out
 
 
-def stitch_iteration(imageL, imageR, max_percentage=20):
+def stitch_iteration(imageL, imageR, max_percentage=20, threads=1):
     """One iteration of the reference driver (CPU/main.cpp:72-92): Stitchtools::prepare -> flow prepare -> setBlend ->
-    generateNovelView -> setMergedmiddle -> Gather.  Returns (FinalResult, dict of intermediates)."""
+    generateNovelView -> setMergedmiddle -> Gather.  Returns (FinalResult, dict of intermediates).
+    threads > 1: the blend map and the two flow directions -- independent computations the reference runs one after the
+    other -- run on separate host threads (ctypes releases the GIL); the results are identical."""
     m, oL, oR = stitch_match_and_mask(imageL, imageR)
-    braw, md = stitch_blend_raw(m)
+    if threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as ex:
+            fut = ex.submit(lambda: stitch_blend_raw(m))
+            fLR, fRL = prepare_bidirectional(oL, oR, max_percentage, threads=2)
+            braw, md = fut.result()
+    else:
+        braw, md = stitch_blend_raw(m)
+        fLR, fRL = prepare_bidirectional(oL, oR, max_percentage)
     blend = stitch_blend_smooth(braw, md)
-    fLR, fRL = prepare_bidirectional(oL, oR, max_percentage)
     merged = combine_novel_views(oL, oR, fLR, fRL, blend)
     final = stitch_gather(imageL, imageR, merged, m)
     return final, dict(map=m, overlappedL=oL, overlappedR=oR, blend_raw=braw, merged_dis=md, blend=blend,

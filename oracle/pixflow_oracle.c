@@ -28,6 +28,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <pthread.h>
 #include <string.h>
 #ifdef __SSE2__
 #include <emmintrin.h>
@@ -424,23 +425,32 @@ static inline float error_function(const SweepCtx* c, int x, int y, float fx, fl
 
 /* one pixel of a sweep: CPU/PixFlow.hpp:317-322 (forward) / :330-335 (backward), with
  * proposeFlowUpdate :342-362 and errorGradient :364-386 inlined */
+#ifdef ORC_STATS
+/* analysis build only (tools/sweep_adoption_stats.py): which pixels adopt a neighbour's proposal */
+static unsigned char* g_stats_adopt = 0;
+ORC_API double orc_stats[8];   /* [0] warp-steps with an active pixel, [1] of them with no adopter among the neighbours, [2] active px, [3] adopting px */
+#define ORC_STATS_ADOPT(v) if (g_stats_adopt) g_stats_adopt[(size_t)y * w + x] |= (v)
+#else
+#define ORC_STATS_ADOPT(v)
+#endif
 static inline void sweep_pixel(const SweepCtx* c, float* flow, int x, int y, int dir) {
     const int w = c->w, h = c->h;
     float* f = flow + ((size_t)y * w + x) * 2;
     float currErr = error_function(c, x, y, f[0], f[1]);
+    ORC_STATS_ADOPT(4);
     const int hasX = dir > 0 ? (x > 0) : (x < w - 1);
     const int hasY = dir > 0 ? (y > 0) : (y < h - 1);
     if (hasX) {
         const float* p = flow + ((size_t)y * w + (x - dir)) * 2;
         const float px = p[0], py = p[1];
         const float e = error_function(c, x, y, px, py);
-        if (e < currErr) { f[0] = px; f[1] = py; currErr = e; }
+        if (e < currErr) { f[0] = px; f[1] = py; currErr = e; ORC_STATS_ADOPT(1); }
     }
     if (hasY) {
         const float* p = flow + ((size_t)(y - dir) * w + x) * 2;
         const float px = p[0], py = p[1];
         const float e = error_function(c, x, y, px, py);
-        if (e < currErr) { f[0] = px; f[1] = py; currErr = e; }
+        if (e < currErr) { f[0] = px; f[1] = py; currErr = e; ORC_STATS_ADOPT(2); }
     }
     const float ex = error_function(c, x, y, f[0] + K_GRAD_EPSILON, f[1] + 0.0f);
     const float ey = error_function(c, x, y, f[0] + 0.0f, f[1] + K_GRAD_EPSILON);
@@ -455,6 +465,9 @@ ORC_API void orc_sweep(const float* alpha0, const float* alpha1, const float* I0
                        const float* I1x, const float* I1y, const float* blurred, float* flow,
                        int h, int w, int dir) {
     SweepCtx c = { w, h, I0x, I0y, I1x, I1y, blurred };
+#ifdef ORC_STATS
+    g_stats_adopt = (unsigned char*)calloc((size_t)h * w, 1);
+#endif
     if (dir > 0) {
         for (int y = 0; y < h; ++y)
             for (int x = 0; x < w; ++x)
@@ -466,6 +479,28 @@ ORC_API void orc_sweep(const float* alpha0, const float* alpha1, const float* I0
                 if (alpha0[(size_t)y * w + x] > K_UPDATE_ALPHA_THRESHOLD && alpha1[(size_t)y * w + x] > K_UPDATE_ALPHA_THRESHOLD)
                     sweep_pixel(&c, flow, x, y, -1);
     }
+#ifdef ORC_STATS
+    {   /* the GPU sweep's grouping: R = 16 consecutive logical rows per warp, row g handles logical column s - g at step s */
+        const int R = 16;
+        for (int jw = 0; jw < h; jw += R)
+            for (int s = 0; s < w + R - 1; ++s) {
+                int any_active = 0, miss = 0;
+                for (int g = 0; g < R && jw + g < h; ++g) {
+                    const int i = s - g, j = jw + g;
+                    if (i < 0 || i >= w) continue;
+                    const int x = dir > 0 ? i : w - 1 - i, y = dir > 0 ? j : h - 1 - j;
+                    const unsigned char me = g_stats_adopt[(size_t)y * w + x];
+                    if (!(me & 4)) continue;
+                    any_active = 1;
+                    orc_stats[2] += 1; if (me & 3) orc_stats[3] += 1;
+                    if (i > 0 && (g_stats_adopt[(size_t)y * w + (x - dir)] & 3)) miss = 1;
+                    if (j > 0 && (g_stats_adopt[(size_t)(y - dir) * w + x] & 3)) miss = 1;
+                }
+                if (any_active) { orc_stats[0] += 1; if (!miss) orc_stats[1] += 1; }
+            }
+        free(g_stats_adopt); g_stats_adopt = 0;
+    }
+#endif
 }
 
 /* CPU/PixFlow.hpp:388-405 lowAlphaFlowDiffusion (blur + blend) */
@@ -672,6 +707,24 @@ ORC_API int orc_compute_flow(const uint8_t* i0, size_t stride0, const uint8_t* i
     return 0;
 }
 
+typedef struct {
+    const uint8_t *i0, *i1;
+    int rows, cols, pc, len, max_percentage, hint;
+    float* out;
+} DirJob;
+static int g_prepare_threads = 1;
+
+/* one direction of prepare: flow on the padded pair, then the crop of CPU/OpticalFlow.cpp:143-144 */
+static void* dir_job_run(void* arg) {
+    DirJob* j = (DirJob*)arg;
+    float* f = (float*)malloc(sizeof(float) * (size_t)j->rows * j->pc * 2);
+    orc_compute_flow(j->i0, (size_t)j->pc * 4, j->i1, (size_t)j->pc * 4, j->rows, j->pc, j->max_percentage, j->hint, f, 0, 0);
+    for (int y = 0; y < j->rows; ++y)
+        memcpy(j->out + (size_t)y * j->cols * 2, f + ((size_t)y * j->pc + j->len) * 2, sizeof(float) * (size_t)j->cols * 2);
+    free(f);
+    return 0;
+}
+
 /* NovelViewGeneratorAsymmetricFlow::prepare, CPU/OpticalFlow.cpp:102-145: circular pad by
  * cols/20, flow(L,R,LEFT), flow(R,L,RIGHT), crop.  Outputs rows x cols x 2 floats each. */
 ORC_API int orc_prepare_bidirectional(const uint8_t* L, size_t strideL, const uint8_t* R, size_t strideR,
@@ -690,17 +743,26 @@ ORC_API int orc_prepare_bidirectional(const uint8_t* L, size_t strideL, const ui
             memcpy(d + (size_t)(len + cols) * 4, s, (size_t)len * 4);
         }
     }
-    float* f = (float*)malloc(sizeof(float) * (size_t)rows * pc * 2);
+    /* the two directions are independent computations (CPU/OpticalFlow.cpp:130-139 runs them one after the other): with
+     * threads == 2 they run on two host threads -- same arithmetic, same results, half the wall time of the checker */
+    DirJob jobs[2];
     for (int dirn = 0; dirn < 2; ++dirn) {
-        if (dirn == 0) orc_compute_flow(pad[0], (size_t)pc * 4, pad[1], (size_t)pc * 4, rows, pc, max_percentage, HINT_LEFT, f, 0, 0);
-        else orc_compute_flow(pad[1], (size_t)pc * 4, pad[0], (size_t)pc * 4, rows, pc, max_percentage, HINT_RIGHT, f, 0, 0);
-        float* out = dirn == 0 ? flowLR : flowRL;
-        for (int y = 0; y < rows; ++y)
-            memcpy(out + (size_t)y * cols * 2, f + ((size_t)y * pc + len) * 2, sizeof(float) * (size_t)cols * 2);
+        jobs[dirn].i0 = pad[dirn]; jobs[dirn].i1 = pad[1 - dirn];
+        jobs[dirn].rows = rows; jobs[dirn].cols = cols; jobs[dirn].pc = pc; jobs[dirn].len = len;
+        jobs[dirn].max_percentage = max_percentage;
+        jobs[dirn].hint = dirn == 0 ? HINT_LEFT : HINT_RIGHT;
+        jobs[dirn].out = dirn == 0 ? flowLR : flowRL;
     }
-    free(f); free(pad[0]); free(pad[1]);
+    pthread_t th;
+    const int threaded = g_prepare_threads >= 2 && pthread_create(&th, 0, dir_job_run, &jobs[1]) == 0;
+    dir_job_run(&jobs[0]);
+    if (threaded) pthread_join(th, 0); else dir_job_run(&jobs[1]);
+    free(pad[0]); free(pad[1]);
     return 0;
 }
+
+/* 1 (default): the two flows of orc_prepare_bidirectional run one after the other on the calling thread; 2: concurrently */
+ORC_API void orc_set_prepare_threads(int n) { g_prepare_threads = n; }
 
 /* NovelViewUtil::generateNovelViewPoint, CPU/OpticalFlow.cpp:9-28 */
 static inline const uint8_t* novel_view_point(const uint8_t* img, size_t stride, const float* flow,

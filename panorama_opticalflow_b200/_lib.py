@@ -21,6 +21,9 @@ SIGNATURES = {
     "pf_prepare_bidirectional": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz]),
     "pf_prepare_bidirectional_batch": (_i, [_vp, _i, C.POINTER(_vp), _sz, C.POINTER(_vp), _sz, _i, _i,
                                             C.POINTER(_vp), _sz, C.POINTER(_vp), _sz]),
+    "pf_prepare_bidirectional_batch_async": (_i, [_vp, _i, _i, C.POINTER(_vp), _sz, C.POINTER(_vp), _sz, _i, _i,
+                                                  C.POINTER(_vp), _sz, C.POINTER(_vp), _sz]),
+    "pf_wait": (_i, [_vp, _i]),
     "pf_combine_novel_views": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz]),
     "pf_novel_view": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz]),
     "pf_stitch_prepare": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),

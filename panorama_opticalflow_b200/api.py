@@ -30,8 +30,9 @@ def _is_device_tensor(a):
     return hasattr(a, "data_ptr") and hasattr(a, "is_cuda")
 
 
-def _view(a, dtype, channels, name):
-    """-> (keepalive, pointer, row_stride_bytes, rows, cols)"""
+def _view(a, dtype, channels, name, out=False):
+    """-> (keepalive, pointer, row_stride_bytes, rows, cols).  Inputs whose pixels are not densely packed are copied;
+    an OUTPUT (out=True) must be usable in place -- a copy would leave the caller's buffer unfilled -- so it raises."""
     if _is_device_tensor(a):
         if not a.is_cuda:
             a = a.numpy()
@@ -51,8 +52,19 @@ def _view(a, dtype, channels, name):
     item = a.itemsize
     inner_ok = a.strides[-1] == item and (channels == 1 or a.strides[1] == item * channels)
     if not inner_ok or a.strides[0] < a.shape[1] * item * channels:
+        if out:
+            raise ValueError("%s is an output and must have densely packed pixels and non-overlapping rows" % name)
         a = np.ascontiguousarray(a)
+    if out and not a.flags.writeable:
+        raise ValueError("%s is an output and must be writeable" % name)
     return a, C.c_void_p(a.ctypes.data), a.strides[0], a.shape[0], a.shape[1]
+
+
+def _same_size(what, size, **others):
+    """every operand of a call must have imageL's (rows, cols): the C ABI trusts the sizes it is given"""
+    for name, sz in others.items():
+        if tuple(sz) != tuple(size):
+            raise ValueError("%s: %s is %d x %d but imageL is %d x %d" % (what, name, sz[0], sz[1], size[0], size[1]))
 
 
 class OpticalFlowInterface:
@@ -69,6 +81,7 @@ class PixFlow(OpticalFlowInterface):
     def __init__(self, flowAlgName, device=-1):
         self._lib = _lib.load()
         self._h = C.c_void_p()
+        self._pending = {}
         self.flowAlgName = flowAlgName
         _lib.check(self._lib.pf_engine_create(flowAlgName.encode(), int(device), C.byref(self._h)))
 
@@ -93,7 +106,7 @@ class PixFlow(OpticalFlowInterface):
             raise ValueError("I0BGRA and I1BGRA must have the same size")
         if flow is None:
             flow = np.empty((rows, cols, 2), np.float32)
-        kf, pf_, sf, rf, cf = _view(flow, np.float32, 2, "flow")
+        kf, pf_, sf, rf, cf = _view(flow, np.float32, 2, "flow", out=True)
         if (rf, cf) != (rows, cols):
             raise ValueError("flow must be (rows, cols, 2)")
         _lib.check(self._lib.pf_compute_flow(self._h, p0, s0, p1, s1, rows, cols, int(hint), pf_, sf))
@@ -109,12 +122,14 @@ class PixFlow(OpticalFlowInterface):
             flowLtoR = np.empty((rows, cols, 2), np.float32)
         if flowRtoL is None:
             flowRtoL = np.empty((rows, cols, 2), np.float32)
-        ka, pa, sa, _, _ = _view(flowLtoR, np.float32, 2, "flowLtoR")
-        kb, pb, sb, _, _ = _view(flowRtoL, np.float32, 2, "flowRtoL")
+        ka, pa, sa, ra, ca = _view(flowLtoR, np.float32, 2, "flowLtoR", out=True)
+        kb, pb, sb, rb, cb = _view(flowRtoL, np.float32, 2, "flowRtoL", out=True)
+        if (ra, ca) != (rows, cols) or (rb, cb) != (rows, cols):
+            raise ValueError("flowLtoR and flowRtoL must be (rows, cols, 2)")
         _lib.check(self._lib.pf_prepare_bidirectional(self._h, pl, sl, pr, sr, rows, cols, pa, sa, pb, sb))
         return ka, kb
 
-    def prepareBidirectionalBatch(self, imagesL, imagesR, flowsLtoR=None, flowsRtoL=None):
+    def prepareBidirectionalBatch(self, imagesL, imagesR, flowsLtoR=None, flowsRtoL=None, slot=None):
         """n independent pairs of identical size, all in flight concurrently on this engine's device."""
         n = len(imagesL)
         vl = [_view(a, np.uint8, 4, "imagesL[%d]" % i) for i, a in enumerate(imagesL)]
@@ -124,42 +139,60 @@ class PixFlow(OpticalFlowInterface):
             flowsLtoR = [np.empty((rows, cols, 2), np.float32) for _ in range(n)]
         if flowsRtoL is None:
             flowsRtoL = [np.empty((rows, cols, 2), np.float32) for _ in range(n)]
-        va = [_view(a, np.float32, 2, "flowsLtoR[%d]" % i) for i, a in enumerate(flowsLtoR)]
-        vb = [_view(a, np.float32, 2, "flowsRtoL[%d]" % i) for i, a in enumerate(flowsRtoL)]
+        va = [_view(a, np.float32, 2, "flowsLtoR[%d]" % i, out=True) for i, a in enumerate(flowsLtoR)]
+        vb = [_view(a, np.float32, 2, "flowsRtoL[%d]" % i, out=True) for i, a in enumerate(flowsRtoL)]
         for group in (vl, vr, va, vb):
             if len(group) != n or any(v[2] != group[0][2] or (v[3], v[4]) != (rows, cols) for v in group):
                 raise ValueError("all pairs of a batch must share size and stride")
         arr = lambda vs: (C.c_void_p * n)(*[v[1].value for v in vs])
-        _lib.check(self._lib.pf_prepare_bidirectional_batch(
-            self._h, n, arr(vl), vl[0][2], arr(vr), vr[0][2], rows, cols, arr(va), va[0][2], arr(vb), vb[0][2]))
+        if slot is None:
+            _lib.check(self._lib.pf_prepare_bidirectional_batch(
+                self._h, n, arr(vl), vl[0][2], arr(vr), vr[0][2], rows, cols, arr(va), va[0][2], arr(vb), vb[0][2]))
+        else:
+            _lib.check(self._lib.pf_prepare_bidirectional_batch_async(
+                self._h, int(slot), n, arr(vl), vl[0][2], arr(vr), vr[0][2], rows, cols, arr(va), va[0][2], arr(vb), vb[0][2]))
+            self._pending[int(slot)] = (vl, vr, va, vb)          # keep the buffers alive until wait(slot)
         return [v[0] for v in va], [v[0] for v in vb]
+
+    def prepareBidirectionalBatchAsync(self, slot, imagesL, imagesR, flowsLtoR, flowsRtoL):
+        """pf_prepare_bidirectional_batch_async: returns at once; the flows are complete after wait(slot).  slot is 0 or 1."""
+        return self.prepareBidirectionalBatch(imagesL, imagesR, flowsLtoR, flowsRtoL, slot=slot)
+
+    def wait(self, slot):
+        _lib.check(self._lib.pf_wait(self._h, int(slot)))
+        self._pending.pop(int(slot), None)
 
     def combineNovelViews(self, imageL, imageR, flowLtoR, flowRtoL, blend, out=None):
         kl, pl, sl, rows, cols = _view(imageL, np.uint8, 4, "imageL")
-        kr, pr, sr, _, _ = _view(imageR, np.uint8, 4, "imageR")
-        ka, pa, sa, _, _ = _view(flowLtoR, np.float32, 2, "flowLtoR")
-        kb, pb, sb, _, _ = _view(flowRtoL, np.float32, 2, "flowRtoL")
-        kc, pc, sc, _, _ = _view(blend, np.float32, 1, "blend")
+        kr, pr, sr, r1, c1 = _view(imageR, np.uint8, 4, "imageR")
+        ka, pa, sa, r2, c2 = _view(flowLtoR, np.float32, 2, "flowLtoR")
+        kb, pb, sb, r3, c3 = _view(flowRtoL, np.float32, 2, "flowRtoL")
+        kc, pc, sc, r4, c4 = _view(blend, np.float32, 1, "blend")
         if out is None:
             out = np.empty((rows, cols, 4), np.uint8)
-        ko, po, so, _, _ = _view(out, np.uint8, 4, "out")
+        ko, po, so, r5, c5 = _view(out, np.uint8, 4, "out", out=True)
+        _same_size("combineNovelViews", (rows, cols), imageR=(r1, c1), flowLtoR=(r2, c2), flowRtoL=(r3, c3), blend=(r4, c4), out=(r5, c5))
         _lib.check(self._lib.pf_combine_novel_views(self._h, pl, sl, pr, sr, pa, sa, pb, sb, pc, sc, rows, cols, po, so))
         return ko
 
     def novelView(self, imageL, imageR, blend, out=None, flowLtoR=None, flowRtoL=None):
         """prepare + setBlend + generateNovelView fused on the device (CPU/main.cpp:82-89)."""
         kl, pl, sl, rows, cols = _view(imageL, np.uint8, 4, "imageL")
-        kr, pr, sr, _, _ = _view(imageR, np.uint8, 4, "imageR")
-        kc, pc, sc, _, _ = _view(blend, np.float32, 1, "blend")
+        kr, pr, sr, r1, c1 = _view(imageR, np.uint8, 4, "imageR")
+        kc, pc, sc, r2, c2 = _view(blend, np.float32, 1, "blend")
         if out is None:
             out = np.empty((rows, cols, 4), np.uint8)
-        ko, po, so, _, _ = _view(out, np.uint8, 4, "out")
+        ko, po, so, r3, c3 = _view(out, np.uint8, 4, "out", out=True)
+        sizes = dict(imageR=(r1, c1), blend=(r2, c2), out=(r3, c3))
         pa = pb = C.c_void_p()
         sa = sb = 0
         if flowLtoR is not None:
-            ka, pa, sa, _, _ = _view(flowLtoR, np.float32, 2, "flowLtoR")
+            ka, pa, sa, r4, c4 = _view(flowLtoR, np.float32, 2, "flowLtoR", out=True)
+            sizes["flowLtoR"] = (r4, c4)
         if flowRtoL is not None:
-            kb, pb, sb, _, _ = _view(flowRtoL, np.float32, 2, "flowRtoL")
+            kb, pb, sb, r5, c5 = _view(flowRtoL, np.float32, 2, "flowRtoL", out=True)
+            sizes["flowRtoL"] = (r5, c5)
+        _same_size("novelView", (rows, cols), **sizes)
         _lib.check(self._lib.pf_novel_view(self._h, pl, sl, pr, sr, pc, sc, rows, cols, po, so, pa, sa, pb, sb))
         return ko
 
@@ -341,7 +374,7 @@ def stitch_iteration(flowAlg, colorImageL, colorImageR, out=None, want_intermedi
         raise ValueError("colorImageL and colorImageR must have the same size")
     if out is None:
         out = np.empty((rows, cols, 4), np.uint8)
-    ko, po, so, r2, c2 = _view(out, np.uint8, 4, "out")
+    ko, po, so, r2, c2 = _view(out, np.uint8, 4, "out", out=True)
     if (rows, cols) != (r2, c2) or (not _is_device_tensor(out) and ko is not out):
         raise ValueError("out must be a dense (rows, cols, 4) uint8 buffer of the canvas size")
     null = C.c_void_p(None)

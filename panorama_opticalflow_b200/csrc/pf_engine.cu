@@ -116,6 +116,8 @@ struct Workspace {
     cudaStream_t sMain = nullptr, sDir[2] = {nullptr, nullptr};
     cudaEvent_t evReady = nullptr, evDone[2] = {nullptr, nullptr};
     cudaEvent_t evIn = nullptr;                   // host inputs staged (recorded on the engine's copy stream)
+    cudaEvent_t evOut = nullptr;                  // host outputs copied back (recorded on the engine's download stream)
+    bool outPending = false;                      // evOut must be waited for before the results are complete
     std::vector<cudaEvent_t> sweepEv[2];          // optional timing events
     size_t nSweepEv[2] = {0, 0};
     // the whole pair pipeline (front end -> both directions -> join) captured once as a CUDA graph and replayed
@@ -144,7 +146,8 @@ struct Workspace {
         Ipre = nullptr; merged = nullptr; blend = nullptr;
         if (evReady) cudaEventDestroy(evReady);
         if (evIn) cudaEventDestroy(evIn);
-        sMain = nullptr; evReady = nullptr; evIn = nullptr;
+        if (evOut) cudaEventDestroy(evOut);
+        sMain = nullptr; evReady = nullptr; evIn = nullptr; evOut = nullptr; outPending = false;
     }
 
     int init(int rows, int cols, int pad, int idx = 0) {
@@ -188,6 +191,7 @@ struct Workspace {
         sMain = sDir[0];   // the shared front end runs on direction 0's stream: two streams (hardware queues) per pair
         PF_CUDA(cudaEventCreateWithFlags(&evReady, cudaEventDisableTiming));
         PF_CUDA(cudaEventCreateWithFlags(&evIn, cudaEventDisableTiming));
+        PF_CUDA(cudaEventCreateWithFlags(&evOut, cudaEventDisableTiming));
         return PF_OK;
     }
 };
@@ -209,6 +213,11 @@ struct pf_engine {
     // uploads of a batch interleave on the DMA engine and every pair's inputs complete only when all have, which idles the
     // GPU for the whole upload; in FIFO order pair 0 starts computing after its own 2 images have arrived.
     cudaStream_t sCopy = nullptr;
+    // ... and host OUTPUTS leave through one download stream of their own (second DMA engine): the D2H of a pair never sits
+    // in front of another pair's kernels, and with the asynchronous calls the downloads of batch k overlap the compute of
+    // batch k+1 (which runs on the other slot's workspaces).
+    cudaStream_t sOut = nullptr;
+    std::vector<Workspace*> inflight[2];          // workspaces of the last asynchronous batch of each slot (pf_wait)
     cudaEvent_t evT0 = nullptr, evT1 = nullptr;
 
     ~pf_engine() {
@@ -217,6 +226,7 @@ struct pf_engine {
         if (evT1) cudaEventDestroy(evT1);
         if (sTimer) cudaStreamDestroy(sTimer);
         if (sCopy) cudaStreamDestroy(sCopy);
+        if (sOut) cudaStreamDestroy(sOut);
     }
 
     // workspace #idx for the given geometry (created or re-created on demand)
@@ -445,15 +455,27 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
             PF_CUDA(cudaGraphLaunch(w.graph, st));
             LAUNCHED(w.graph_launches);
         }
+        bool host_out = false;
         for (int d = 0; d < ndir; ++d) {
             dflow[d] = w.out[d];
             dfstride[d] = (size_t)w.plan.cols * sizeof(float2);
-            if (outs[d])
+            if (outs[d] && is_device_ptr(outs[d]))
                 PF_CUDA(cudaMemcpy2DAsync(outs[d], ostrides[d], w.out[d], dfstride[d], (size_t)w.plan.cols * sizeof(float2),
-                                          w.plan.rows, cudaMemcpyDefault, st));
+                                          w.plan.rows, cudaMemcpyDeviceToDevice, st));
+            else if (outs[d]) host_out = true;
         }
         PF_CUDA(cudaEventRecord(w.evDone[0], st));
         if (ndir == 2) PF_CUDA(cudaEventRecord(w.evDone[1], st));
+        if (host_out) {      // downloads on the engine's own D2H stream, behind this pair's compute only
+            if (!e->sOut) PF_CUDA(cudaStreamCreateWithFlags(&e->sOut, cudaStreamNonBlocking));
+            PF_CUDA(cudaStreamWaitEvent(e->sOut, w.evDone[0], 0));
+            for (int d = 0; d < ndir; ++d)
+                if (outs[d] && !is_device_ptr(outs[d]))
+                    PF_CUDA(cudaMemcpy2DAsync(outs[d], ostrides[d], w.out[d], dfstride[d], (size_t)w.plan.cols * sizeof(float2),
+                                              w.plan.rows, cudaMemcpyDeviceToHost, e->sOut));
+            PF_CUDA(cudaEventRecord(w.evOut, e->sOut));
+            w.outPending = true;
+        }
         return PF_OK;
     }
     if ((rc = stage_input(w, 0, imgL, strideL, &dimg[0], &dstride[0], w.sMain)) != PF_OK) return rc;
@@ -475,6 +497,7 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
 int sync_pair(Workspace& w, int ndir) {
     for (int d = 0; d < ndir; ++d) PF_CUDA(cudaStreamSynchronize(w.sDir[d]));
     PF_CUDA(cudaStreamSynchronize(w.sMain));
+    if (w.outPending) { PF_CUDA(cudaEventSynchronize(w.evOut)); w.outPending = false; }
     return PF_OK;
 }
 
@@ -546,6 +569,8 @@ void pf_engine_destroy(pf_engine* e) {
             if (!w) continue;
             for (int d = 0; d < 2; ++d) if (w->sDir[d]) cudaStreamSynchronize(w->sDir[d]);
         }
+        if (e->sOut) cudaStreamSynchronize(e->sOut);
+        if (e->sCopy) cudaStreamSynchronize(e->sCopy);
         delete e;
     }
 }
@@ -582,6 +607,8 @@ int pf_timer_stop(pf_engine* e, double* ms) {
         PF_CUDA(cudaStreamSynchronize(w->sMain));
         for (int d = 0; d < 2; ++d) PF_CUDA(cudaStreamSynchronize(w->sDir[d]));
     }
+    if (e->sCopy) PF_CUDA(cudaStreamSynchronize(e->sCopy));
+    if (e->sOut) PF_CUDA(cudaStreamSynchronize(e->sOut));
     PF_CUDA(cudaEventRecord(e->evT1, e->sTimer));
     PF_CUDA(cudaEventSynchronize(e->evT1));
     float f = 0.0f;
@@ -589,6 +616,8 @@ int pf_timer_stop(pf_engine* e, double* ms) {
     *ms = f;
     return PF_OK;
 }
+
+static int wait_slot_locked(pf_engine* e, int slot);
 
 int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, size_t s1, int rows, int cols, int hint,
                     void* flow_out, size_t flow_stride) {
@@ -602,6 +631,7 @@ int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, siz
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard g(e->device);
     Workspace* w;
+    if ((rc = wait_slot_locked(e, 0)) != PF_OK) return rc;        // an asynchronous batch may still own workspace 0
     if ((rc = e->workspace(0, rows, cols, 0, &w)) != PF_OK) return rc;
     const int hints[2] = {hint, 0};
     void* outs[2] = {flow_out, nullptr};
@@ -613,9 +643,40 @@ int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, siz
     return collect_sweep_timing(e, used);
 }
 
-int pf_prepare_bidirectional_batch(pf_engine* e, int n, const void* const* Ls, size_t sl, const void* const* Rs, size_t sr,
-                                   int rows, int cols, void* const* lr, size_t slr, void* const* rl, size_t srl) {
-    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+// workspace index of pair i of slot s: the two slots own disjoint workspaces (streams, graphs, staging and output buffers)
+static inline int ws_index(int slot, int i) { return 2 * i + slot; }
+
+static int wait_slot_locked(pf_engine* e, int slot) {
+    int rc = PF_OK;
+    for (Workspace* w : e->inflight[slot]) {
+        const int r = sync_pair(*w, 2);
+        if (r != PF_OK && rc == PF_OK) rc = r;
+    }
+    if (rc == PF_OK) rc = collect_sweep_timing(e, e->inflight[slot]);
+    e->inflight[slot].clear();
+    return rc;
+}
+
+static int batch_enqueue_locked(pf_engine* e, int slot, int n, const void* const* Ls, size_t sl, const void* const* Rs, size_t sr,
+                                int rows, int cols, void* const* lr, size_t slr, void* const* rl, size_t srl) {
+    int rc;
+    if (!e->inflight[slot].empty() && (rc = wait_slot_locked(e, slot)) != PF_OK) return rc;    // the slot's buffers are re-used
+    const int pad = cols / 20;   // CPU/OpticalFlow.cpp:113
+    const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};   // CPU/OpticalFlow.cpp:130-139
+    for (int i = 0; i < n; ++i) {
+        Workspace* w;
+        if ((rc = e->workspace(ws_index(slot, i), rows, cols, pad, &w)) != PF_OK) return rc;
+        e->inflight[slot].push_back(w);
+        void* outs[2] = {lr[i], rl[i]};
+        const size_t ostr[2] = {slr, srl};
+        const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
+        if ((rc = enqueue_pair(e, *w, Ls[i], sl, Rs[i], sr, 2, hints, outs, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
+    }
+    return PF_OK;
+}
+
+static int batch_check_args(int n, const void* const* Ls, size_t sl, const void* const* Rs, size_t sr, int rows, int cols,
+                            void* const* lr, size_t slr, void* const* rl, size_t srl) {
     if (n <= 0 || !Ls || !Rs || !lr || !rl) return fail(PF_ERR_INVALID_ARGUMENT, "bad batch arguments");
     int rc;
     for (int i = 0; i < n; ++i) {
@@ -624,33 +685,50 @@ int pf_prepare_bidirectional_batch(pf_engine* e, int n, const void* const* Ls, s
         if ((rc = check_image_args(lr[i], slr, rows, cols, 8, "flowLtoR")) != PF_OK) return rc;
         if ((rc = check_image_args(rl[i], srl, rows, cols, 8, "flowRtoL")) != PF_OK) return rc;
     }
-    const int pad = cols / 20;   // CPU/OpticalFlow.cpp:113
+    const int pad = cols / 20;
     if ((int)((float)(cols + 2 * pad) * 0.5f) < 4 || (int)((float)rows * 0.5f) < 4) return fail(PF_ERR_INVALID_ARGUMENT, "image too small");
+    return PF_OK;
+}
+
+int pf_prepare_bidirectional_batch_async(pf_engine* e, int slot, int n, const void* const* Ls, size_t sl, const void* const* Rs, size_t sr,
+                                         int rows, int cols, void* const* lr, size_t slr, void* const* rl, size_t srl) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    if (slot < 0 || slot > 1) return fail(PF_ERR_INVALID_ARGUMENT, "slot must be 0 or 1");
+    int rc;
+    if ((rc = batch_check_args(n, Ls, sl, Rs, sr, rows, cols, lr, slr, rl, srl)) != PF_OK) return rc;
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard g(e->device);
-    std::vector<Workspace*> used;
+    return batch_enqueue_locked(e, slot, n, Ls, sl, Rs, sr, rows, cols, lr, slr, rl, srl);
+}
+
+int pf_wait(pf_engine* e, int slot) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    if (slot < 0 || slot > 1) return fail(PF_ERR_INVALID_ARGUMENT, "slot must be 0 or 1");
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
+    return wait_slot_locked(e, slot);
+}
+
+int pf_prepare_bidirectional_batch(pf_engine* e, int n, const void* const* Ls, size_t sl, const void* const* Rs, size_t sr,
+                                   int rows, int cols, void* const* lr, size_t slr, void* const* rl, size_t srl) {
+    if (!e) return fail(PF_ERR_INVALID_ARGUMENT, "engine is NULL");
+    int rc;
+    if ((rc = batch_check_args(n, Ls, sl, Rs, sr, rows, cols, lr, slr, rl, srl)) != PF_OK) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    DeviceGuard g(e->device);
     const auto t_begin = std::chrono::steady_clock::now();
-    const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};   // CPU/OpticalFlow.cpp:130-139
-    for (int i = 0; i < n; ++i) {
-        Workspace* w;
-        if ((rc = e->workspace(i, rows, cols, pad, &w)) != PF_OK) return rc;
-        used.push_back(w);
-        void* outs[2] = {lr[i], rl[i]};
-        const size_t ostr[2] = {slr, srl};
-        const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
-        if ((rc = enqueue_pair(e, *w, Ls[i], sl, Rs[i], sr, 2, hints, outs, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
-    }
+    if ((rc = batch_enqueue_locked(e, 0, n, Ls, sl, Rs, sr, rows, cols, lr, slr, rl, srl)) != PF_OK) return rc;
     const auto t_enq = std::chrono::steady_clock::now();
-    for (Workspace* w : used)
-        if ((rc = sync_pair(*w, 2)) != PF_OK) return rc;
+    rc = wait_slot_locked(e, 0);
     if (getenv("PF_DEBUG_TIMING")) {
         const auto t_end = std::chrono::steady_clock::now();
         fprintf(stderr, "[pf] batch n=%d: enqueue %.2f ms, wait %.2f ms\n", n,
                 std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
                 std::chrono::duration<double, std::milli>(t_end - t_enq).count());
     }
-    return collect_sweep_timing(e, used);
+    return rc;
 }
+
 
 int pf_prepare_bidirectional(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, int rows, int cols,
                              void* lr, size_t slr, void* rl, size_t srl) {
@@ -701,6 +779,7 @@ int pf_combine_novel_views(pf_engine* e, const void* L, size_t sl, const void* R
     std::lock_guard<std::mutex> lk(e->mu);
     DeviceGuard g(e->device);
     Workspace* w;
+    if ((rc = wait_slot_locked(e, 0)) != PF_OK) return rc;
     if ((rc = e->workspace(0, rows, cols, cols / 20, &w)) != PF_OK) return rc;
     cudaStream_t st = w->sMain;
     const uint8_t* dimg[2]; size_t dstr[2];
@@ -727,6 +806,7 @@ static int novel_view_locked(pf_engine* e, const void* L, size_t sl, const void*
     int rc;
     Workspace* w;
     const int pad = cols / 20;
+    if ((rc = wait_slot_locked(e, 0)) != PF_OK) return rc;
     if ((rc = e->workspace(0, rows, cols, pad, &w)) != PF_OK) return rc;
     const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};
     void* outs[2] = {lr, rl};

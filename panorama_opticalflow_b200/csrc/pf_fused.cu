@@ -31,11 +31,13 @@ constexpr int MH = MTH + 2 * MR;         // 12
 
 enum { MODE_PLAIN = 0, MODE_PREP = 1, MODE_DIFFUSE = 2 };
 
-// BORDER_REFLECT_101 with a single reflection, then clamped (exact for -n < p < 2n-1, any valid index otherwise)
+// BORDER_REFLECT_101: one branch-free reflection covers -n < p < 2n-1 (every halo position when n > 7); images narrower
+// than the blur radius (half-resolution sides 4..7) need repeated reflections and take the looping form.
 __device__ __forceinline__ int reflect1_clamped(int p, int n) {
     p = p < 0 ? -p : p;
     p = p >= n ? 2 * n - 2 - p : p;
-    return clampi(p, 0, n - 1);
+    if ((unsigned)p >= (unsigned)n) p = reflect101(p, n);
+    return p;
 }
 
 // 15x15 sigma 8 Gaussian of the 2-channel flow: row pass left-to-right over the 15 taps, column pass in the symmetric
@@ -52,8 +54,6 @@ k_blur15(const float2* __restrict__ flow, float2* __restrict__ out, int h, int w
     const int tx = threadIdx.x, ty = threadIdx.y;
     const f2p* fl = reinterpret_cast<const f2p*>(flow);
     {   // tile + halo: each thread fetches (up to) 2 columns x 3 rows; reflect-101 indices computed once per thread.
-        // One reflection suffices for every position a valid output needs (w, h > 7); positions only reached by
-        // out-of-image threads are clamped.
         const int gx0 = reflect1_clamped(x0 - BR + tx, w), gx1 = reflect1_clamped(x0 - BR + tx + TILE, w);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -155,6 +155,7 @@ PrepArgs make_prep(const float* alpha0, const float* alpha1, const float2* G0, c
     pa.R = 32 / sweep_lanes_per_row();
     pa.logR = pa.R == 4 ? 2 : (pa.R == 8 ? 3 : (pa.R == 16 ? 4 : 5));
     pa.dir = dir;
+    pa.slow = 0;       // set by the launchers from the level width
     return pa;
 }
 
@@ -167,7 +168,9 @@ void launch_blur15(const float2* flow, float2* blurred, int h, int w, cudaStream
 
 void launch_blur15_prep(const float2* flow, float2* blurred, int h, int w, const float* alpha0, const float* alpha1,
                         const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
-    k_blur15<MODE_PREP><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir));
+    PrepArgs pa = make_prep(alpha0, alpha1, G0, G1, rec, dir);
+    pa.slow = exact_div_width_ok(w) ? 0 : 1;
+    k_blur15<MODE_PREP><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, pa);
 }
 
 void launch_blur15_diffuse(const float2* flow, float2* out, int h, int w, const float* alpha0, const float* alpha1, cudaStream_t st) {
@@ -183,7 +186,9 @@ void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t s
 
 void launch_median5_prep(const float2* src, float2* dst, const float2* blurred, int h, int w, const float* alpha0,
                          const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
-    k_median5<MODE_PREP><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, blurred, h, w, make_prep(alpha0, alpha1, G0, G1, rec, dir));
+    PrepArgs pa = make_prep(alpha0, alpha1, G0, G1, rec, dir);
+    pa.slow = exact_div_width_ok(w) ? 0 : 1;
+    k_median5<MODE_PREP><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, blurred, h, w, pa);
 }
 
 }  // namespace pf

@@ -186,8 +186,13 @@ namespace pf {
 
 // Validity ranges of the branch-free sequences below (checked exhaustively by pf_selftest_exact_math):
 //   sqrt_exact_fast(a):     a == 0 or 2^-60 <= a < 2^126
-//   div_by_const(x, d, rd): x == 0 or 2^-60 <= |x| < 2^100, for d = 0.001f and every integer d in [24, 16384]
+//   div_by_const(x, d, rd): x == 0 or 2^-60 <= |x| < 2^100, for d = 0.001f and every integer d in [PF_EXACT_W_MIN, PF_EXACT_W_MAX]
+// Level widths outside that interval (inputs narrower than 48 px, or wider than 16384 px after the half-scale) make the
+// launchers select the IEEE-intrinsic path for every pixel (exact_div_width_ok).
 #define PF_TINY_BITS 0x21800000u      /* float bits of 2^-60 */
+#define PF_EXACT_W_MIN 24
+#define PF_EXACT_W_MAX 8192
+__host__ __device__ __forceinline__ bool exact_div_width_ok(int w) { return w >= PF_EXACT_W_MIN && w <= PF_EXACT_W_MAX; }
 __device__ __forceinline__ bool in_sqrt_range(float a) { return a == 0.0f || (a >= 0x1p-60f && a < 0x1p126f); }
 __device__ __forceinline__ bool in_div_range(float x) { const float a = fabsf(x); return a == 0.0f || (a >= 0x1p-60f && a < 0x1p100f); }
 // key of a non-negative operand for the "tiny but non-zero" test: min over keys < PF_TINY_BITS-1  <=>  some

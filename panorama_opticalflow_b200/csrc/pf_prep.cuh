@@ -12,6 +12,7 @@ struct PrepArgs {
     SweepRec* rec;                           // wavefront-packed output
     int R, logR;                             // rows per sweep warp (4, 16 or 32) and its log2
     int dir;                                 // +1 forward sweep, -1 backward sweep
+    int slow;                                // 1: level width outside the verified range of div_by_const -> IEEE intrinsics everywhere
 };
 
 __device__ __forceinline__ ErrCtx make_err_ctx(const float2* G1, int w, int h) {
@@ -112,7 +113,7 @@ __device__ __forceinline__ void emit_record(const PrepArgs& a, const ErrCtx& c, 
         // operands outside the verified range of the branch-free sequences: tiny non-zero (key test), or huge / inf / NaN
         // (every operand is bounded by the errors, so testing those is enough -- same test as the sweep kernel's)
         const float vmax = fmaxf(fmaxf(fabsf(e0), fabsf(ex)), fabsf(ey));
-        const bool bad = (tiny < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f) || !(e0 == e0) || !(ex == ex) || !(ey == ey);
+        const bool bad = a.slow || (tiny < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f) || !(e0 == e0) || !(ex == ex) || !(ey == ey);
         if (bad) {                                   // rare: IEEE intrinsics
             unsigned dummy = 0;
             e0 = err_from_g1<true>(c, rcp_w, g0, bl, g1a, f.x, f.y, dummy);

@@ -105,6 +105,13 @@ __device__ __forceinline__ int ld_volatile_global_s32(const int* p) {
     asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// acquire load at gpu scope: pairs with st_release_global_s32 below (the producer's blend stores happen-before everything the
+// CTA does after the bar.sync that follows the poll)
+__device__ __forceinline__ int ld_acquire_global_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_volatile_global_s32(int* p, int v) {
     asm volatile("st.volatile.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
@@ -174,10 +181,10 @@ k_stitch_block_blur(BlockBlurArgs a) {
             const int need = min(bx + a.rx + 1, a.nbx);
             if (tid < a.ry && by - 1 - tid >= 0)             // thread j watches row by-1-j; the last value seen is kept, so a
                 while (seen < need) {                         // row that is far ahead is polled once, not once per block
-                    seen = ld_volatile_global_s32(a.progress + by - 1 - tid);
+                    seen = ld_acquire_global_s32(a.progress + by - 1 - tid);
                     if (seen < need) __nanosleep(64);
                 }
-            __syncthreads();       // no fence: the window is read with ld.cg (L2), never from this SM's L1
+            __syncthreads();       // release (producer) / acquire (poll above) + this barrier order the window reads below
             // ---- window of the current image: batches of 8 independent L2 loads per thread, stored to shared memory afterwards
             // (a load-then-store loop would serialise on the L2 latency, which dominated the per-block time) ----
             const int x = bx * a.step;

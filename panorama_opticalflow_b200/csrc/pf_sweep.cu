@@ -140,6 +140,7 @@ void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G
     pa.R = 32 / sweep_lanes_per_row();
     pa.logR = pa.R == 4 ? 2 : (pa.R == 8 ? 3 : (pa.R == 16 ? 4 : 5));
     pa.dir = dir;
+    pa.slow = exact_div_width_ok(w) ? 0 : 1;
     k_sweep_prep<<<g, b, 0, st>>>(blurred, flow, h, w, pa);
 }
 
@@ -559,7 +560,7 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
     k.rcp_w = __frcp_rn(k.fw); k.rcp_eps = __frcp_rn(PF_GRAD_EPS);
     asm volatile("" : "+r"(w), "+r"(k.pitch), "+r"(k.dstep), "+r"(k.g1s_last));     // keep loop invariants in registers
     asm volatile("" : "+f"(k.wm2), "+f"(k.hm2), "+f"(k.fw), "+f"(k.rcp_w), "+f"(k.rcp_eps));
-    const float NEG_INF = __int_as_float(0xff800000);
+    const bool force_slow = !exact_div_width_ok(w);      // level width outside the verified range of div_by_const
     const float yf = (float)y;
     float xf = (float)(DIR > 0 ? -g : w - 1 + g);                  // float(x) of step 0, then +-1 per step (exact)
     float2* flow_row = a.flow + (size_t)y * w;
@@ -614,14 +615,14 @@ __device__ __noinline__ void sweep_block(const Sweep2Args& a, SweepSmem<P>& sm, 
             up.y = g == 0 ? __uint_as_float(v.z) : up.y;
         }
         const bool valid = rowValid && (unsigned)i < (unsigned)w;
-        const bool active = valid && A.x > NEG_INF;
+        const bool active = valid && __float_as_uint(A.x) != 0xff800000u;     // -inf marks "not updatable"; a NaN E(f0) stays active
         float2 out = make_float2(A.y, A.z);
         if (__any_sync(full, active)) {           // warp-uniform: skip fully inactive stretches
             unsigned tkey = 0xffffffffu;
             float vmax = 0.0f;
             out = step_eval<POSX, P, false>(k, xf, yf, A, B, res, up, i, j, sub, gbase, tkey, vmax);
             // operands left the range of the branch-free sequences (tiny non-zero, or huge / inf / NaN)?
-            const bool bad = (tkey < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f);
+            const bool bad = force_slow || (tkey < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f);
             // rare: redo the step with the IEEE intrinsics -- out of line, so that the hot loop stays compact in the instruction cache
             if (__any_sync(full, bad && active)) out = step_eval_slow<POSX, P>(k, xf, yf, A, B, res, up, i, j, sub, gbase);
         }

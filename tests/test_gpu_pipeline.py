@@ -125,9 +125,60 @@ def test_reference_style_generator_roundtrip(orc):
     gen.close()
 
 
+def test_full_size_config2_bit_exact_vs_oracle(orc, engine_search):
+    """BASELINE configs[1] at the size and on the very pair the headline is quoted on (bench.py: rows 4000 x cols 2000, seed 1,
+    disparity amplitude cols/12 + 1 = 168 px, so the coarse search branch is live): 37 pyramid levels, level-0 1100 x 2000,
+    32 row blocks (more than the 21-CTA wavefront front, so tickets are re-used) and 18 laps of the hand-off rings.  Both flow
+    fields must equal the CPU oracle's bit for bit, the blended image within 1 LSB (about 16 s of CPU for the oracle)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from panorama_opticalflow_b200 import synth
+    rows, cols = 4000, 2000
+    L, R = synth.make_pair(rows, cols, 1, cols / 12.0 + 1.0, False)
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        fut = ex.submit(orc.prepare_bidirectional, L, R, 20)         # the oracle runs while the GPU does (ctypes drops the GIL)
+        got = engine_search.prepareBidirectional(L, R)
+        got = (got[0].copy(), got[1].copy())
+        want = fut.result()
+    assert_bit_equal(got[0], want[0], "4000x2000 flowLtoR")
+    assert_bit_equal(got[1], want[1], "4000x2000 flowRtoL")
+    assert np.abs(got[0][..., 0]).max() > 100.0          # the 168 px disparity was actually recovered
+    blend = synth.make_blend(rows, cols)
+    merged = engine_search.combineNovelViews(L, R, got[0], got[1], blend)
+    wm = orc.combine_novel_views(L, R, want[0], want[1], blend)
+    d = np.abs(merged.astype(int) - wm.astype(int))
+    assert d.max() <= RGB_TOL_LSB, "merged differs by %d LSB" % d.max()
+    assert np.array_equal(merged[..., 3], wm[..., 3])
+
+
+def test_wide_level_bit_exact_vs_oracle(orc, engine_search):
+    """A pair whose level-0 width (1430, through prepare's pad) exceeds every other parity case: x / float(w) on the sweep's
+    critical path uses the exactly rounded division by a constant for w in [24, 8192] (tests/test_gpu_exact_math.py)."""
+    from panorama_opticalflow_b200 import synth
+    L, R = synth.make_pair(120, 2600, 5, 30.0, False)
+    want = orc.prepare_bidirectional(L, R, 20)
+    got = engine_search.prepareBidirectional(L, R)
+    assert_bit_equal(got[0], want[0], "wide flowLtoR")
+    assert_bit_equal(got[1], want[1], "wide flowRtoL")
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (9, 15), (15, 10), (12, 40), (40, 13), (47, 47)])
+def test_tiny_images_vs_oracle(orc, engine_low, shape):
+    """Half-resolution sides of 4..7 px: the 15 x 15 blur needs repeated reflect-101 reflections there, and level widths
+    below 24 are outside the verified range of the division by a constant (IEEE-intrinsic path)."""
+    rows, cols = shape
+    rng = np.random.default_rng(rows * 100 + cols)
+    L = rng.integers(0, 256, (rows, cols, 4), dtype=np.uint8)
+    R = np.roll(L, 1, axis=1)
+    L[..., 3] = 255
+    R[..., 3] = 255
+    want = orc.compute_flow(L, R, 0, 3)
+    got = engine_low.computeOpticalFlow(L, R, 3)
+    assert_bit_equal(got, want, "tiny %dx%d" % shape)
+
+
 def test_full_size_properties(engine_search, engine_low):
-    """BASELINE config 2 size (rows 4000 x cols 2000): the oracle takes too long here, so check size-independent
-    properties: determinism (bit-identical reruns), the flow recovers the synthetic disparity, and -- for
+    """BASELINE config 2 size (rows 4000 x cols 2000), size-independent properties next to the bit-exact comparison above:
+    determinism (bit-identical reruns), the flow recovers the synthetic disparity, and -- for
     pixflow_low, where the hint is unused -- swapping the pair swaps the two flow fields exactly."""
     from panorama_opticalflow_b200 import synth
     rows, cols = 4000, 2000
@@ -168,3 +219,40 @@ def test_stream_path_equals_graph_path(orc, engine_search):
         assert_bit_equal(b, c, "stream path")
     again = engine_search.prepareBidirectional(L, R)     # replay of the cached graph
     assert_bit_equal(again[0], want[0], "graph replay")
+
+
+def test_async_batches_on_two_slots(orc, engine_search):
+    """pf_prepare_bidirectional_batch_async / pf_wait: two batches in flight on the two slots (pinned host buffers, uploads and
+    downloads on their own streams), then a slot is re-used without an explicit wait.  Every flow equals the oracle's."""
+    import torch
+    from panorama_opticalflow_b200 import synth
+    rows, cols, n = 110, 150, 3
+    pairs = [synth.make_pair(rows, cols, 90 + i, 6.0 + i, i == 1) for i in range(2 * n)]
+    want = [orc.prepare_bidirectional(L, R, 20) for L, R in pairs]
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    hL = [pin(p[0]) for p in pairs]
+    hR = [pin(p[1]) for p in pairs]
+    oLR = [torch.empty((rows, cols, 2), dtype=torch.float32).pin_memory().numpy() for _ in pairs]
+    oRL = [torch.empty((rows, cols, 2), dtype=torch.float32).pin_memory().numpy() for _ in pairs]
+    for rep in range(2):
+        for o in oLR + oRL:
+            o.fill(np.nan)
+        engine_search.prepareBidirectionalBatchAsync(0, hL[:n], hR[:n], oLR[:n], oRL[:n])
+        engine_search.prepareBidirectionalBatchAsync(1, hL[n:], hR[n:], oLR[n:], oRL[n:])
+        engine_search.wait(0)
+        for i in range(n):
+            assert_bit_equal(oLR[i], want[i][0], "slot 0 pair %d LR" % i)
+            assert_bit_equal(oRL[i], want[i][1], "slot 0 pair %d RL" % i)
+        # re-use slot 0 while slot 1 may still be running: swapped outputs, so stale data cannot pass
+        engine_search.prepareBidirectionalBatchAsync(0, hL[n:], hR[n:], oLR[:n], oRL[:n])
+        engine_search.wait(1)
+        engine_search.wait(0)
+        for i in range(n):
+            assert_bit_equal(oLR[n + i], want[n + i][0], "slot 1 pair %d LR" % i)
+            assert_bit_equal(oLR[i], want[n + i][0], "slot 0 (re-used) pair %d LR" % i)
+            assert_bit_equal(oRL[i], want[n + i][1], "slot 0 (re-used) pair %d RL" % i)
+    # a synchronous call after asynchronous ones still works (it waits for slot 0)
+    engine_search.prepareBidirectionalBatchAsync(0, hL[:n], hR[:n], oLR[:n], oRL[:n])
+    g = engine_search.prepareBidirectional(pairs[0][0], pairs[0][1])
+    assert_bit_equal(g[0], want[0][0], "sync after async")
+    engine_search.wait(0)

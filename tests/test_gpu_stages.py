@@ -126,3 +126,27 @@ def test_sweep(orc, case, direction):
     got = stages.sweep(A0, A1, G0, G1, blurred, flow, direction)
     assert_bit_equal(got, want, "sweep dir %+d" % direction)
     assert not np.array_equal(want, flow)
+
+
+@pytest.mark.parametrize("direction", [+1, -1])
+def test_sweep_with_nan_and_inf_flows(orc, direction):
+    """Non-finite flows cannot arise from 8-bit inputs, but the sweep must still follow the reference on them: a pixel whose
+    own error is NaN stays updatable (no proposal can win against NaN, the gradient step writes NaN) and hands NaN on;
+    inf / huge flows leave the range of the branch-free exact sequences and take the IEEE-intrinsic path."""
+    from panorama_opticalflow_b200 import stages
+    I0, I1, A0, A1 = _pair_planes(orc, 200, 260, 7, 8.0, False, 0)
+    G0, G1 = _grad(orc, I0), _grad(orc, I1)
+    h, w = I0.shape
+    rng = np.random.default_rng(7)
+    flow = (rng.standard_normal((h, w, 2)) * 0.7).astype(np.float32)
+    for k, v in enumerate((np.nan, np.inf, -np.inf, 1e30, 1e-42, -0.0)):
+        ys, xs = rng.integers(0, h, 12), rng.integers(0, w, 12)
+        flow[ys, xs, k % 2] = v
+    blurred = orc.gaussian_blur(np.nan_to_num(flow, nan=0.0, posinf=0.0, neginf=0.0), 15, 8.0)
+    want = orc.sweep(A0, A1, G0[..., 0], G0[..., 1], G1[..., 0], G1[..., 1], blurred, flow, direction)
+    got = stages.sweep(A0, A1, G0, G1, blurred, flow, direction)
+    assert np.isnan(want).any()
+    # NaN payloads are not part of the contract: compare NaN-ness, and bits everywhere else
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    m = ~np.isnan(want)
+    assert np.array_equal(got[m].view(np.uint32), want[m].view(np.uint32)), int((got[m].view(np.uint32) != want[m].view(np.uint32)).sum())
