@@ -5,6 +5,7 @@ The product is the CUDA library csrc/ -> libpixflow_b200.so (C-ABI: include/pixf
 is its Python host-side mirror.  Importing it does not need a GPU; creating an engine does.
 """
 from .api import (DirectionHint, NovelViewGenerator, NovelViewGeneratorAsymmetricFlow, NovelViewUtil,  # noqa: F401
-                  OpticalFlowInterface, PixFlow, PixFlowError, Stitchtools, makeOpticalFlowByName, stitch_iteration)
+                  OpticalFlowInterface, PixFlow, PixFlowError, Stitchtools, four_input_frontend, makeOpticalFlowByName,
+                  stitch_iteration)
 
 __version__ = "0.1.0"

@@ -389,17 +389,24 @@ def stitch_iteration(flowAlg, colorImageL, colorImageR, out=None, want_intermedi
     return (out, extra) if want_intermediates else out
 
 
-def four_input_frontend(flowAlg, colorImage1, colorImage2, colorImage3, colorImage4):
-    """The input preparation of the 4-input driver (CPU_4Input/main.cpp:64-79) -> (colorImageL, colorImageR)."""
+def four_input_frontend(flowAlg, colorImage1, colorImage2, colorImage3, colorImage4, device_out=False):
+    """The input preparation of the 4-input driver (CPU_4Input/main.cpp:64-79) -> (colorImageL, colorImageR).
+    device_out=True (CUDA tensor inputs): the two outputs are CUDA tensors and nothing crosses PCIe."""
     views = [_view(a, np.uint8, 4, "colorImage%d" % (k + 1)) for k, a in enumerate((colorImage1, colorImage2, colorImage3, colorImage4))]
     rows, cols = views[0][3], views[0][4]
     if any((v[3], v[4]) != (rows, cols) for v in views) or any(v[2] != views[0][2] for v in views):
         raise ValueError("the four inputs must have the same size and row stride")
     ptrs = (C.c_void_p * 4)(*[v[1] for v in views])
-    L = np.empty((rows, cols, 4), np.uint8)
-    R = np.empty((rows, cols, 4), np.uint8)
-    _lib.check(flowAlg._lib.pf_four_input_frontend(flowAlg._h, ptrs, views[0][2], rows, cols, C.c_void_p(L.ctypes.data), cols * 4,
-                                                   C.c_void_p(R.ctypes.data), cols * 4))
+    if device_out:
+        import torch
+        L = torch.empty((rows, cols, 4), dtype=torch.uint8, device=colorImage1.device)
+        R = torch.empty_like(L)
+        pl, pr = C.c_void_p(L.data_ptr()), C.c_void_p(R.data_ptr())
+    else:
+        L = np.empty((rows, cols, 4), np.uint8)
+        R = np.empty((rows, cols, 4), np.uint8)
+        pl, pr = C.c_void_p(L.ctypes.data), C.c_void_p(R.ctypes.data)
+    _lib.check(flowAlg._lib.pf_four_input_frontend(flowAlg._h, ptrs, views[0][2], rows, cols, pl, cols * 4, pr, cols * 4))
     return L, R
 
 

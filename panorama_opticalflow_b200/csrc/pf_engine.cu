@@ -88,7 +88,7 @@ struct Plan {
             skew_total += (pf::skew_elems(skew.back()) + 63) & ~(size_t)63;
             for (int s = 0; s < 2; ++s) {
                 bnd_off.push_back(bnd_lines);
-                bnd_lines += pf::sweep2_boundary_lines(hs[l], ws[l], pf::sweep2_use_smem(ws[l]));
+                bnd_lines += pf::sweep2_boundary_lines(hs[l], ws[l]);
             }
         }
     }
@@ -118,6 +118,8 @@ struct Workspace {
     cudaEvent_t evIn = nullptr;                   // host inputs staged (recorded on the engine's copy stream)
     cudaEvent_t evOut = nullptr;                  // host outputs copied back (recorded on the engine's download stream)
     bool outPending = false;                      // evOut must be waited for before the results are complete
+    cudaEvent_t preWait = nullptr;                // (borrowed) event the pair's first operation must wait for, consumed by enqueue_pair
+    cudaEvent_t evNovel = nullptr;                // novel view complete (recorded on sMain by the asynchronous form)
     std::vector<cudaEvent_t> sweepEv[2];          // optional timing events
     size_t nSweepEv[2] = {0, 0};
     // the whole pair pipeline (front end -> both directions -> join) captured once as a CUDA graph and replayed
@@ -147,6 +149,8 @@ struct Workspace {
         if (evReady) cudaEventDestroy(evReady);
         if (evIn) cudaEventDestroy(evIn);
         if (evOut) cudaEventDestroy(evOut);
+        if (evNovel) cudaEventDestroy(evNovel);
+        evNovel = nullptr; preWait = nullptr;
         sMain = nullptr; evReady = nullptr; evIn = nullptr; evOut = nullptr; outPending = false;
     }
 
@@ -192,6 +196,7 @@ struct Workspace {
         PF_CUDA(cudaEventCreateWithFlags(&evReady, cudaEventDisableTiming));
         PF_CUDA(cudaEventCreateWithFlags(&evIn, cudaEventDisableTiming));
         PF_CUDA(cudaEventCreateWithFlags(&evOut, cudaEventDisableTiming));
+        PF_CUDA(cudaEventCreateWithFlags(&evNovel, cudaEventDisableTiming));
         return PF_OK;
     }
 };
@@ -318,7 +323,6 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
         sa.G1s = w.Gs[i1] + p.skew_off[l];
         sa.s = p.skew[l];
         sa.g1s_last = (long long)pf::skew_elems(p.skew[l]) - 1;
-        sa.smem_ll = 1;
         // blur of the incoming flow (the sweeps regularise against it) + records of the forward sweep
         pf::launch_blur15_prep(flow, w.blurred[d], h, wd, A0, A1, G0, G1, w.rec[d], +1, st);
         // forward sweep, in place on `flow`
@@ -399,6 +403,10 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
                  int ndir, const int hints[2], void* outs[2], const size_t ostrides[2],
                  const uint8_t* dimg[2], size_t dstride[2], float2* dflow[2], size_t dfstride[2]) {
     int rc;
+    if (w.preWait) {            // inputs produced on another stream of this library (the stitching step)
+        PF_CUDA(cudaStreamWaitEvent(w.sDir[0], w.preWait, 0));
+        w.preWait = nullptr;
+    }
     if (e->use_graphs && !e->time_sweeps) {
         // ---- graph path: inputs -> staging buffers, one graph launch, outputs <- workspace flow buffers ----
         cudaStream_t st = w.sDir[0];
@@ -801,13 +809,17 @@ int pf_combine_novel_views(pf_engine* e, const void* L, size_t sl, const void* R
 }
 
 // body of pf_novel_view; e->mu held by the caller, arguments already checked
+// inputs_ready / blend_ready: optional events (the images / the blend map are produced on another stream); done: when given,
+// the call does not wait -- *done is the event to wait for (device-side chaining by the stitching step)
 static int novel_view_locked(pf_engine* e, const void* L, size_t sl, const void* R, size_t sr, const void* blend, size_t sb,
-                             int rows, int cols, void* out, size_t so, void* lr, size_t slr, void* rl, size_t srl) {
+                             int rows, int cols, void* out, size_t so, void* lr, size_t slr, void* rl, size_t srl,
+                             cudaEvent_t inputs_ready = nullptr, cudaEvent_t blend_ready = nullptr, cudaEvent_t* done = nullptr) {
     int rc;
     Workspace* w;
     const int pad = cols / 20;
     if ((rc = wait_slot_locked(e, 0)) != PF_OK) return rc;
     if ((rc = e->workspace(0, rows, cols, pad, &w)) != PF_OK) return rc;
+    w->preWait = inputs_ready;
     const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};
     void* outs[2] = {lr, rl};
     const size_t ostr[2] = {slr, srl};
@@ -815,8 +827,14 @@ static int novel_view_locked(pf_engine* e, const void* L, size_t sl, const void*
     if ((rc = enqueue_pair(e, *w, L, sl, R, sr, 2, hints, outs, ostr, dimg, dstr, dflow, dfs)) != PF_OK) return rc;
     // join both directions into sMain, then blend there
     for (int d = 0; d < 2; ++d) PF_CUDA(cudaStreamWaitEvent(w->sMain, w->evDone[d], 0));
+    if (blend_ready) PF_CUDA(cudaStreamWaitEvent(w->sMain, blend_ready, 0));
     if ((rc = combine_impl(e, w, w->sMain, dimg[0], dstr[0], dimg[1], dstr[1], dflow[0], dfs[0], dflow[1], dfs[1],
                            blend, sb, rows, cols, out, so)) != PF_OK) return rc;
+    if (done) {
+        PF_CUDA(cudaEventRecord(w->evNovel, w->sMain));
+        *done = w->evNovel;
+        return PF_OK;
+    }
     if ((rc = sync_pair(*w, 2)) != PF_OK) return rc;
     std::vector<Workspace*> used{w};
     return collect_sweep_timing(e, used);
@@ -846,9 +864,12 @@ struct StitchBufs {
     float *braw = nullptr, *mdis = nullptr, *blend = nullptr;
     void* scratch = nullptr;
     cudaStream_t st = nullptr;                 // the stitching kernels' own (non-blocking) stream
+    cudaEvent_t evMasked = nullptr, evBlend = nullptr;     // OverlappedL/R ready; Blend ready
     void release() {
         std::lock_guard<std::mutex> cg(g_capture_mu);
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
+        if (evMasked) { cudaEventDestroy(evMasked); evMasked = nullptr; }
+        if (evBlend) { cudaEventDestroy(evBlend); evBlend = nullptr; }
         cudaFree(L); cudaFree(R); cudaFree(map); cudaFree(oL); cudaFree(oR); cudaFree(merged); cudaFree(gmap); cudaFree(result);
         cudaFree(braw); cudaFree(mdis); cudaFree(blend); cudaFree(scratch);
         L = R = map = oL = oR = merged = gmap = result = nullptr; braw = mdis = blend = nullptr; scratch = nullptr;
@@ -866,6 +887,8 @@ struct StitchBufs {
         const size_t sb = pf::stitch_smooth_scratch_bytes(r, c);
         PF_CUDA(cudaMalloc(&scratch, sb ? sb : 16));
         PF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        PF_CUDA(cudaEventCreateWithFlags(&evMasked, cudaEventDisableTiming));
+        PF_CUDA(cudaEventCreateWithFlags(&evBlend, cudaEventDisableTiming));
         rows = r; cols = c;
         return PF_OK;
     }
@@ -900,6 +923,7 @@ static int stitch_prepare_dev(StitchBufs& sb, const uint8_t* dL, size_t sl, cons
                               bool smooth, cudaStream_t st) {
     const size_t c1 = (size_t)cols, c4 = (size_t)cols * 4;
     pf::launch_stitch_match_mask(dL, sl, dR, sr, rows, cols, sb.map, c1, sb.oL, c4, sb.oR, c4, st);
+    PF_CUDA(cudaEventRecord(sb.evMasked, st));
     pf::launch_stitch_blend_raw(sb.map, c1, rows, cols, sb.braw, c4, sb.mdis, c4, st);
     LAUNCHED(2);
     if (smooth) {
@@ -908,6 +932,7 @@ static int stitch_prepare_dev(StitchBufs& sb, const uint8_t* dL, size_t sl, cons
         if (n == 0) return fail(PF_ERR_INVALID_ARGUMENT, "blend smoothing: unsupported image shape");
         LAUNCHED(n);
     }
+    PF_CUDA(cudaEventRecord(sb.evBlend, st));
     PF_CUDA(cudaGetLastError());
     return PF_OK;
 }
@@ -1038,9 +1063,13 @@ int pf_stitch_iteration(pf_engine* e, const void* L, size_t sl, const void* R, s
     RC(stage_u8(R, sr, rows, c4, sb.R, &pR, &psr, st));
     // Stitchtools::prepare (CPU/main.cpp:72-73)
     RC(stitch_prepare_dev(sb, pL, psl, pR, psr, rows, cols, true, st));
-    PF_CUDA(cudaStreamSynchronize(st));
-    // NovelViewGeneratorAsymmetricFlow::prepare + setBlend + generateNovelView (:82-89), everything device-resident
-    RC(novel_view_locked(e, sb.oL, c4, sb.oR, c4, sb.blend, c4, rows, cols, sb.merged, c4, nullptr, 0, nullptr, 0));
+    // NovelViewGeneratorAsymmetricFlow::prepare + setBlend + generateNovelView (:82-89), everything device-resident and chained
+    // on the device: the two flows start as soon as OverlappedL/R exist and run concurrently with GenerateBlend (the blend map
+    // is only needed by the final warp + blend); no host synchronisation until the result is complete
+    cudaEvent_t novel_done = nullptr;
+    RC(novel_view_locked(e, sb.oL, c4, sb.oR, c4, sb.blend, c4, rows, cols, sb.merged, c4, nullptr, 0, nullptr, 0,
+                         sb.evMasked, sb.evBlend, &novel_done));
+    PF_CUDA(cudaStreamWaitEvent(st, novel_done, 0));
     // setMergedmiddle + Gather (:93-95)
     pf::launch_stitch_gather(pL, psl, pR, psr, sb.merged, c4, sb.map, (size_t)cols, rows, cols, sb.gmap, sb.result, c4, st);
     LAUNCHED(2);
@@ -1161,8 +1190,7 @@ int pf_stage_sweep(const float* alpha0, const float* alpha1, const float* G0, co
     RC(a0.upload(alpha0, n * 4)); RC(a1.upload(alpha1, n * 4));
     RC(g0.upload(G0, n * 8)); RC(g1.upload(G1, n * 8)); RC(bl.upload(blurred, n * 8)); RC(f.upload(flow, n * 8));
     RC(g1s.alloc(ne * 8)); RC(ra.alloc(pf::sweep_rec_count(h, w) * sizeof(pf::SweepRec)));
-    const bool sm = pf::sweep2_use_smem(w);
-    const size_t lines = pf::sweep2_boundary_lines(h, w, sm);
+    const size_t lines = pf::sweep2_boundary_lines(h, w);
     RC(bnd.alloc(lines * 16)); RC(tk.alloc(16));
     PF_CUDA(cudaMemset(bnd.p, 0, lines * 16)); PF_CUDA(cudaMemset(tk.p, 0, 16));
     pf::launch_skew_copy_f2(g1.as<float2>(), g1s.as<float2>(), sk, 0);
@@ -1170,7 +1198,7 @@ int pf_stage_sweep(const float* alpha0, const float* alpha1, const float* G0, co
                           ra.as<pf::SweepRec>(), h, w, dir, 0);
     pf::Sweep2Args sa;
     sa.rec = ra.as<pf::SweepRec>(); sa.G1s = g1s.as<float2>(); sa.flow = f.as<float2>();
-    sa.s = sk; sa.g1s_last = (long long)ne - 1; sa.boundary = bnd.as<uint4>(); sa.ticket = tk.as<int>(); sa.smem_ll = sm ? 1 : 0;
+    sa.s = sk; sa.g1s_last = (long long)ne - 1; sa.boundary = bnd.as<uint4>(); sa.ticket = tk.as<int>();
     pf::launch_sweep2(sa, dir, 0);
     LAUNCHED(3);
     return f.download(flow, n * 8);

@@ -149,16 +149,6 @@ inline dim3 blur_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + BT
 const dim3 kBlurBlock(TILE, BTY);
 inline dim3 median_grid(int w, int h) { return dim3((w + TILE - 1) / TILE, (h + MTH - 1) / MTH); }
 
-PrepArgs make_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir) {
-    PrepArgs pa;
-    pa.alpha0 = alpha0; pa.alpha1 = alpha1; pa.G0 = G0; pa.G1 = G1; pa.rec = rec;
-    pa.R = 32 / sweep_lanes_per_row();
-    pa.logR = pa.R == 4 ? 2 : (pa.R == 8 ? 3 : (pa.R == 16 ? 4 : 5));
-    pa.dir = dir;
-    pa.slow = 0;       // set by the launchers from the level width
-    return pa;
-}
-
 }  // namespace
 
 void launch_blur15(const float2* flow, float2* blurred, int h, int w, cudaStream_t st) {
@@ -168,8 +158,7 @@ void launch_blur15(const float2* flow, float2* blurred, int h, int w, cudaStream
 
 void launch_blur15_prep(const float2* flow, float2* blurred, int h, int w, const float* alpha0, const float* alpha1,
                         const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
-    PrepArgs pa = make_prep(alpha0, alpha1, G0, G1, rec, dir);
-    pa.slow = exact_div_width_ok(w) ? 0 : 1;
+    const PrepArgs pa = make_prep_args(alpha0, alpha1, G0, G1, rec, w, dir);
     k_blur15<MODE_PREP><<<blur_grid(w, h), kBlurBlock, 0, st>>>(flow, blurred, h, w, pa);
 }
 
@@ -186,8 +175,7 @@ void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t s
 
 void launch_median5_prep(const float2* src, float2* dst, const float2* blurred, int h, int w, const float* alpha0,
                          const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st) {
-    PrepArgs pa = make_prep(alpha0, alpha1, G0, G1, rec, dir);
-    pa.slow = exact_div_width_ok(w) ? 0 : 1;
+    const PrepArgs pa = make_prep_args(alpha0, alpha1, G0, G1, rec, w, dir);
     k_median5<MODE_PREP><<<median_grid(w, h), dim3(TILE, MTH), 0, st>>>(src, dst, blurred, h, w, pa);
 }
 

@@ -33,7 +33,8 @@ void launch_skew_copy_f2(const float2* src, float2* dst, const Skew& s, cudaStre
 // per-pixel records for one sweep, in the wavefront-packed layout the sweep streams through shared memory:
 // a = {E(f0), r0.x, r0.y, -} (own-flow terms; {-inf, f0} where alpha <= 0.9), b = {I0x, I0y, blurred.x, blurred.y}.
 struct __align__(16) SweepRec { float4 a, b; };
-int sweep_lanes_per_row();                // 2 (default), 8 or 1; env PF_SWEEP_LANES
+constexpr int SWEEP_GROUP_ROWS = 16;      // logical rows per sweep warp (two lanes per row)
+int sweep_nsteps_pad(int w);              // wavefront steps of a row group, rounded up to whole TMA stages
 size_t sweep_rec_count(int h, int w);     // SweepRec elements a (h x w) level needs
 void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
                        const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st);
@@ -57,10 +58,8 @@ struct Sweep2Args {
     Skew s;
     uint4* boundary;      // LL lines {fx, flag, fy, flag}, zero-initialised (sweep2_boundary_lines of them)
     int* ticket;          // zero-initialised block ticket counter
-    int smem_ll;          // 1: warp-to-warp lines inside a CTA live in shared memory
 };
-bool sweep2_use_smem(int w);
-size_t sweep2_boundary_lines(int h, int w, bool smem_ll);
+size_t sweep2_boundary_lines(int h, int w);
 void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st);
 
 // ---- inter-level upsample (CPU/PixFlow.hpp:123-124): INTER_CUBIC 32FC2 + "*= 1/0.9" --------------------

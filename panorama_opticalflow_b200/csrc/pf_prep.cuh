@@ -10,10 +10,12 @@ struct PrepArgs {
     const float* alpha0; const float* alpha1;
     const float2* G0; const float2* G1;      // row-major gradients of image 0 (at the pixel) and image 1 (gathered)
     SweepRec* rec;                           // wavefront-packed output
-    int R, logR;                             // rows per sweep warp (4, 16 or 32) and its log2
+    int nsteps_pad;                          // wavefront steps per row group in the record layout (sweep_nsteps_pad(w))
     int dir;                                 // +1 forward sweep, -1 backward sweep
     int slow;                                // 1: level width outside the verified range of div_by_const -> IEEE intrinsics everywhere
 };
+
+PrepArgs make_prep_args(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int w, int dir);
 
 __device__ __forceinline__ ErrCtx make_err_ctx(const float2* G1, int w, int h) {
     ErrCtx c;
@@ -86,7 +88,7 @@ __device__ __forceinline__ float err_from_g1(const ErrCtx& c, float rcp_w, float
 // Record {E(f0), r0.x, r0.y, - | I0x, I0y, blur.x, blur.y} of pixel (x,y) with old flow f and blurred flow bl
 // (CPU/PixFlow.hpp:318 currErr, :321 + :364-386 the gradient step taken when no proposal wins); pixels that the sweep
 // must not update (alpha <= 0.9, :317) get {-inf, f}.  Stored in the wavefront-packed order of the sweep kernel:
-//     rec[((rowblock * nsteps + step) * R + row_in_block)],  nsteps = w + R - 1, step = logical column + row_in_block
+//     rec[((rowgroup * nsteps_pad + step) * 16 + row_in_group)],  step = logical column + row_in_group
 __device__ __forceinline__ void emit_record(const PrepArgs& a, const ErrCtx& c, int x, int y, int w, int h, float2 f, float2 bl) {
     const size_t p = (size_t)y * w + x;
     const float2 g0 = a.G0[p];
@@ -127,8 +129,8 @@ __device__ __forceinline__ void emit_record(const PrepArgs& a, const ErrCtx& c, 
         A.z = fsub(f.y, fmul(PF_GRAD_STEP, q.y));
     }
     const int j = a.dir > 0 ? y : h - 1 - y, i = a.dir > 0 ? x : w - 1 - x;
-    const int wb = j >> a.logR, g = j & (a.R - 1);              // R = rows per sweep warp, a power of two
-    const size_t idx = (((size_t)wb * (w + a.R - 1) + (i + g)) << a.logR) + g;
+    const int wb = j >> 4, g = j & 15;                          // sweep warp (16 logical rows) and row within it
+    const size_t idx = (((size_t)wb * a.nsteps_pad + (i + g)) << 4) + g;
     SweepRec r;
     r.a = A;
     r.b = make_float4(g0.x, g0.y, bl.x, bl.y);

@@ -1,5 +1,5 @@
 """Runs one level-sized sweep (prep + wavefront) through the diagnostic stage entry point, for ncu captures:
-    ncu --set full --clock-control none --import-source on -k regex:k_sweep2 -c 2 -o gpurun_out/sweep python tools/profile_sweep.py
+    ncu --set full --clock-control none --import-source on -k regex:k_sweep -c 2 -o gpurun_out/sweep python tools/profile_sweep.py [h w reps]
 """
 import os
 import sys
