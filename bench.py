@@ -37,6 +37,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout must carry exactly ONE JSON line.  Libraries write banners straight to file descriptor 1 (NCCL's "NCCL version ..."
+# ignores NCCL_DEBUG_FILE), so fd 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor.
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 METRIC = "Mpix/s bidirectional flow (2000x4000 pair)"
 UNIT = "Mpix/s"
 SWEEP_BYTES_PER_PX = 48          # alpha0, alpha1, I0x, I0y, I1x, I1y, blurred(8) read + flow r/w(16)
@@ -233,7 +251,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -323,7 +341,7 @@ def run_stitch_workload(args):
                        "timed": "every input's H2D from pinned host memory + Stitchtools::prepare + both flows + blend + Gather, canvas resident in HBM between iterations; PNG decode/encode outside (%.1f s to decode the packed inputs on the host)" % load_s,
                        "reference_published": "README.md:10-12: 'less than 30 s' for this stitch on an unspecified GPU"},
             "vs_shipped_final_result": cmp_shipped, "gpu_launches": int(launches)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
 
 
@@ -519,7 +537,7 @@ def run_b200(args, rank, world, local_rank):
                 "fraction_of_device_resident_value": e2e_value / value},
         "gpu_launches": int(launches) * world, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -542,6 +560,7 @@ def main():
     ap.add_argument("--crop95", action="store_true", help="four_input: enable the 0.95 row crop of CPU_4Input/main.cpp:82-83")
     ap.add_argument("--save-result", default=None, help="stitch workloads: write FinalResult as PNG here")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

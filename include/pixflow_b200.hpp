@@ -128,6 +128,27 @@ public:
     }
     pf_engine* handle() const { return engine_; }
 
+    // Asynchronous batch of n independent pairs (pf_prepare_bidirectional_batch_async): returns at once, the flows are complete
+    // after wait(slot).  slot is 0 or 1; alternate the slots to overlap the copies of one batch with the compute of the next.
+    // The Mats must stay alive and untouched until wait(slot) returns.  flowsLtoR / flowsRtoL are allocated when empty.
+    void prepareBidirectionalBatchAsync(int slot, const Mat* imagesL, const Mat* imagesR, Mat* flowsLtoR, Mat* flowsRtoL, int n) {
+        if (n <= 0) throw util::VrCamException("prepareBidirectionalBatchAsync: n must be positive");
+        std::unique_ptr<const void*[]> pl(new const void*[n]), pr(new const void*[n]);
+        std::unique_ptr<void*[]> pa(new void*[n]), pb(new void*[n]);
+        for (int i = 0; i < n; ++i) {
+            if (imagesL[i].rows != imagesL[0].rows || imagesL[i].cols != imagesL[0].cols || (size_t)imagesL[i].step != (size_t)imagesL[0].step ||
+                imagesR[i].rows != imagesL[0].rows || imagesR[i].cols != imagesL[0].cols || (size_t)imagesR[i].step != (size_t)imagesR[0].step)
+                throw util::VrCamException("prepareBidirectionalBatchAsync: all pairs of a batch must share size and stride");
+            if (flowsLtoR[i].empty()) flowsLtoR[i] = pf::make_mat(imagesL[0].rows, imagesL[0].cols, pf::PF_32FC2);
+            if (flowsRtoL[i].empty()) flowsRtoL[i] = pf::make_mat(imagesL[0].rows, imagesL[0].cols, pf::PF_32FC2);
+            pl[i] = imagesL[i].data; pr[i] = imagesR[i].data; pa[i] = flowsLtoR[i].data; pb[i] = flowsRtoL[i].data;
+        }
+        pf::check(pf_prepare_bidirectional_batch_async(engine_, slot, n, pl.get(), imagesL[0].step, pr.get(), imagesR[0].step,
+                                                       imagesL[0].rows, imagesL[0].cols, pa.get(), flowsLtoR[0].step, pb.get(),
+                                                       flowsRtoL[0].step));
+    }
+    void wait(int slot) { pf::check(pf_wait(engine_, slot)); }
+
 private:
     pf_engine* engine_ = nullptr;
 };

@@ -65,7 +65,7 @@ def load():
     """Load (building first if needed) and return the ctypes handle with typed signatures."""
     global _lib
     if _lib is None:
-        path = _build.build_lib()
+        path = os.environ.get("PF_LIB_PATH") or _build.build_lib()      # PF_LIB_PATH: a variant build, for experiments only
         if not os.path.exists(path):
             raise ImportError("libpixflow_b200.so is missing and could not be built: " + path)
         lib = C.CDLL(path)

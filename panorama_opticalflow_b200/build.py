@@ -41,10 +41,11 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force=False, verbose=False):
-    if not force and not needs_build():
+def build_lib(force=False, verbose=False, out=None):
+    """out: build a variant (with PF_EXTRA_NVCC_FLAGS) to another path, for experiments (select it with PF_LIB_PATH)"""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("PF_EXTRA_NVCC_FLAGS", "").split() + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("PF_EXTRA_NVCC_FLAGS", "").split() + ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
@@ -53,7 +54,7 @@ def build_lib(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + log)
     if verbose:
         print(log)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

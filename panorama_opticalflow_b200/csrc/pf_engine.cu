@@ -875,17 +875,21 @@ struct StitchBufs {
         L = R = map = oL = oR = merged = gmap = result = nullptr; braw = mdis = blend = nullptr; scratch = nullptr;
         rows = cols = 0;
     }
+    size_t cap_px = 0, cap_scratch = 0;          // capacity: canvases of different sizes alternate without re-allocation
     int ensure(int r, int c) {
         if (r == rows && c == cols) return PF_OK;
+        const size_t need_px = (size_t)r * c, need_scratch = pf::stitch_smooth_scratch_bytes(r, c);
+        if (st && need_px <= cap_px && need_scratch <= cap_scratch) { rows = r; cols = c; return PF_OK; }
         release();
         std::lock_guard<std::mutex> cg(g_capture_mu);
-        const size_t n = (size_t)r * c;
+        const size_t n = need_px > cap_px ? need_px : cap_px;
         PF_CUDA(cudaMalloc(&L, n * 4)); PF_CUDA(cudaMalloc(&R, n * 4)); PF_CUDA(cudaMalloc(&map, n));
         PF_CUDA(cudaMalloc(&oL, n * 4)); PF_CUDA(cudaMalloc(&oR, n * 4)); PF_CUDA(cudaMalloc(&merged, n * 4));
         PF_CUDA(cudaMalloc(&gmap, n)); PF_CUDA(cudaMalloc(&result, n * 4));
         PF_CUDA(cudaMalloc(&braw, n * 4)); PF_CUDA(cudaMalloc(&mdis, n * 4)); PF_CUDA(cudaMalloc(&blend, n * 4));
-        const size_t sb = pf::stitch_smooth_scratch_bytes(r, c);
+        const size_t sb = need_scratch > cap_scratch ? need_scratch : cap_scratch;
         PF_CUDA(cudaMalloc(&scratch, sb ? sb : 16));
+        cap_px = n; cap_scratch = sb;
         PF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         PF_CUDA(cudaEventCreateWithFlags(&evMasked, cudaEventDisableTiming));
         PF_CUDA(cudaEventCreateWithFlags(&evBlend, cudaEventDisableTiming));

@@ -109,6 +109,7 @@ void launch_skew_copy_f2(const float2* src, float2* dst, const Skew& s, cudaStre
 // so everything a warp needs for one step is ONE contiguous run of 512 bytes, four steps are one 2 KB bulk copy, and a
 // warp consumes its runs strictly sequentially.
 // ---------------------------------------------------------------------------------------------------------
+// (rounded up to 4 steps whatever the stage size, so that the record layout does not depend on a tuning knob)
 __host__ __device__ __forceinline__ int sweep_nsteps_pad_dev(int w) { return (w + SWEEP_GROUP_ROWS - 1 + 3) & ~3; }
 int sweep_nsteps_pad(int w) { return sweep_nsteps_pad_dev(w); }
 
@@ -154,8 +155,14 @@ void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G
 #endif
 constexpr int SW_PREFETCH_GATHER = PF_SW_PREFETCH;   // steps ahead for the L1 warm-up of the gradient gather
 constexpr int SW_LL_RING = 64;                       // entries of a shared-memory LL ring (power of two)
-constexpr int SW_STAGE_STEPS = 4;                    // wavefront steps per TMA bulk copy (2 KB)
-constexpr int SW_NSTAGES = 3;                        // stages of a warp's record ring (one being consumed, two in flight)
+#ifndef PF_SW_STAGE_STEPS
+#define PF_SW_STAGE_STEPS 4
+#endif
+#ifndef PF_SW_NSTAGES
+#define PF_SW_NSTAGES 3
+#endif
+constexpr int SW_STAGE_STEPS = PF_SW_STAGE_STEPS;    // wavefront steps per TMA bulk copy (4 -> 2 KB); also the unroll factor
+constexpr int SW_NSTAGES = PF_SW_NSTAGES;            // stages of a warp's record ring (one being consumed, the others in flight)
 constexpr int SW_ROWS = SWEEP_GROUP_ROWS;            // 16 rows per warp, two lanes per row
 constexpr int SW_WARPS = PF_SWEEP_WARPS;             // compute warps per CTA (+ 1 poller warp)
 constexpr int SW_ROWS_PER_CTA = SW_ROWS * SW_WARPS;
@@ -444,7 +451,7 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
         tma_bulk_g2s(rec0 + slot * SW_STAGE_BYTES, stream + (size_t)t * SW_STAGE_BYTES, SW_STAGE_BYTES, full0 + slot * 8);
     };
     if (lane == 0)
-        for (int t = 0; t < SW_NSTAGES - 1 && t < nstages; ++t) issue(t);        // prologue
+        for (int t = 0; t < SW_NSTAGES && t < nstages; ++t) issue(t);            // prologue: every slot
     const unsigned my_rec = pin_i((int)(rec0 + g * (unsigned)sizeof(SweepRec)));
 
     float2 res = make_float2(0.0f, 0.0f);
@@ -461,24 +468,21 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
     const bool storer = sub == 0;
     int s = 0;                                    // wavefront step
 
+    // software pipeline: the records of step s + 1 are fetched at the end of step s (in the shadow of the exchange shuffles)
+    auto load_rec = [&](unsigned addr, float4& A, float4& B) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(A.w) : "r"(addr));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(B.x), "=f"(B.y), "=f"(B.z), "=f"(B.w) : "r"(addr + 16u));
+    };
+    constexpr unsigned STEP_BYTES = SW_ROWS * (unsigned)sizeof(SweepRec);
+    float4 A, B;
+    mbar_wait(full0, 0);
+    load_rec(my_rec, A, B);
+
     for (int t = 0; t < nstages; ++t) {
-        const int slot = t % SW_NSTAGES;
-        {   // refill the slot consumed during the previous iteration with stage t + NSTAGES - 1 (all lanes are past their reads
-            // of it: the loop body below ends with a __syncwarp; the proxy fence orders those reads before the TMA's writes)
-            const int tn = t + SW_NSTAGES - 1;
-            if (lane == 0 && tn < nstages) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(tn);
-            }
-        }
-        mbar_wait(full0 + slot * 8, (t / SW_NSTAGES) & 1);
-        const unsigned srec = my_rec + slot * SW_STAGE_BYTES;
+        const unsigned srec = my_rec + (t % SW_NSTAGES) * SW_STAGE_BYTES;
 #pragma unroll
         for (int u = 0; u < SW_STAGE_STEPS; ++u, ++s) {
             // steps past w + 14 (padding of the last stage) have no valid pixel and fall through the skip below
-            float4 A, B;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(A.w) : "r"(srec + u * (SW_ROWS * (unsigned)sizeof(SweepRec))));
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(B.x), "=f"(B.y), "=f"(B.z), "=f"(B.w) : "r"(srec + u * (SW_ROWS * (unsigned)sizeof(SweepRec)) + 16u));
             // ---- up neighbour: previous result of the row above (shuffle; first row of the warp: LL ring) ----
             float2 up;
             up.x = __shfl_up_sync(full, res.x, 2);
@@ -494,6 +498,7 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
             const bool valid = (unsigned)i < (unsigned)w;
             const bool active = valid && __float_as_uint(A.x) != 0xff800000u;   // -inf marks "not updatable"; a NaN E(f0) stays active
             float2 out = make_float2(A.y, A.z);
+            const float4 Ac = A;
             if (__any_sync(full, active)) {           // warp-uniform: skip fully inactive stretches
                 const float2 g0 = make_float2(B.x, B.y), bl = make_float2(B.z, B.w);
                 const float2 cand = make_float2(sub ? up.x : res.x, sub ? up.y : res.y);
@@ -512,7 +517,11 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
                     eO = __shfl_xor_sync(full, eM, 1);
                 }
                 const float2 other = make_float2(__shfl_xor_sync(full, mine.x, 1), __shfl_xor_sync(full, mine.y, 1));
-                out = select_result(sub ? eO : eM, sub ? other : mine, sub ? eM : eO, sub ? mine : other, i > 0, j > 0, A);
+                // ---- records of the next step (same stage: the address is a compile-time offset) ----
+                if (u + 1 < SW_STAGE_STEPS) load_rec(srec + (u + 1) * STEP_BYTES, A, B);
+                out = select_result(sub ? eO : eM, sub ? other : mine, sub ? eM : eO, sub ? mine : other, i > 0, j > 0, Ac);
+            } else {
+                if (u + 1 < SW_STAGE_STEPS) load_rec(srec + (u + 1) * STEP_BYTES, A, B);
             }
             res.x = valid ? out.x : res.x;
             res.y = valid ? out.y : res.y;
@@ -532,8 +541,21 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
             fptr += DIR;
             ++gptr;
         }
+        // ---- stage boundary: every lane holds its last records of stage t in registers ----
         __syncwarp();
-        if (lane == 0 && s <= in_cols) st_volatile_shared_s32(prog_in, s);       // done with the ring entries of columns < s
+        if (lane == 0) {
+            if (s <= in_cols) st_volatile_shared_s32(prog_in, s);          // done with the ring entries of columns < s
+            const int tn = t + SW_NSTAGES;                                 // refill the slot just consumed (the proxy fence orders
+            if (tn < nstages) {                                            // the warp's reads of it before the TMA's writes)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(tn);
+            }
+        }
+        if (t + 1 < nstages) {
+            const int sn = (t + 1) % SW_NSTAGES;
+            mbar_wait(full0 + sn * 8, ((t + 1) / SW_NSTAGES) & 1);
+            load_rec(my_rec + sn * SW_STAGE_BYTES, A, B);
+        }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
@@ -607,9 +629,22 @@ size_t sweep2_boundary_lines(int h, int w) {
     return (size_t)(ncta > 1 ? ncta - 1 : 0) * (size_t)w + 1;
 }
 
+// Row blocks that work at the same time: block b starts SW_ROWS_PER_CTA steps after block b-1 and lasts w + SW_ROWS_PER_CTA - 1
+// steps, so ceil((w + R - 1) / R) blocks overlap; `margin` more CTAs keep a free CTA ready when a block could start (latency)
+// at the price of CTAs that sit waiting for their turn (SM slots, which is what bounds the throughput with many pairs in flight).
+static int sweep_margin() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("PF_SWEEP_MARGIN");
+        m = e ? atoi(e) : 0;         // measured (profiles/r2_notes.md): 0 / 1 / 2 -> 1253 / 1240 / 1227 Mpix/s at 16 pairs, single pair unchanged
+        if (m < 0 || m > 8) m = 0;
+    }
+    return m;
+}
+
 void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st) {
     const int nblocks = (a.s.h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
-    const int front = (a.s.w + 2 * SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA + 2;   // row blocks working at the same time
+    const int front = (a.s.w + 2 * SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA + sweep_margin();
     const int ncta = nblocks < front ? nblocks : front;
     if (dir > 0) {
         if (a.s.posx) k_sweep<1, 1><<<ncta, SW_THREADS, 0, st>>>(a); else k_sweep<1, 0><<<ncta, SW_THREADS, 0, st>>>(a);

@@ -23,6 +23,27 @@ def _build_exe(tmp_path, name="novel_view_main"):
     return exe
 
 
+@pytest.mark.parametrize("name", ["novel_view_main", "stitch_main"])
+def test_cv_mat_branch_type_checks_against_a_stub_opencv(tmp_path, name):
+    """OpenCV C++ is not installed in this image, so the `#ifdef PIXFLOW_B200_HAVE_OPENCV` branch of pixflow_b200.hpp (Mat =
+    cv::Mat, the reference's own matrix type at the boundary: CPU/OpticalFlow.hpp:34-70) would never be compiled.  A stub
+    <opencv2/core.hpp> with cv::Mat's real member signatures (tests/cpp/stub) makes the compiler check that branch, and the
+    reference-style drivers link against the library through it."""
+    from panorama_opticalflow_b200 import _lib
+    _lib.load()
+    libdir = os.path.dirname(_lib.lib_path())
+    exe = str(tmp_path / (name + "_cv"))
+    probe = tmp_path / "probe.cpp"
+    probe.write_text('#include "pixflow_b200.hpp"\n#ifndef PIXFLOW_B200_HAVE_OPENCV\n#error cv::Mat branch not selected\n#endif\n'
+                     'static_assert(std::is_same<pf::Mat, cv::Mat>::value, "pf::Mat must be cv::Mat");\n'
+                     'static_assert(pf::PF_8UC4 == CV_8UC4 && pf::PF_32FC2 == CV_32FC2 && pf::PF_32FC1 == CV_32FC1 && pf::PF_8UC1 == CV_8UC1, "type codes");\n'
+                     'int main() { return 0; }\n')
+    inc = ["-I", os.path.join(ROOT, "tests", "cpp", "stub"), "-I", os.path.join(ROOT, "include")]
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Werror", "-fsyntax-only"] + inc + ["-include", "type_traits", str(probe)])
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall"] + inc + [os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe,
+                           "-L", libdir, "-lpixflow_b200", "-Wl,-rpath," + libdir])
+
+
 def test_cpp_mirror_compiles_links_and_reports_errors(tmp_path):
     exe = _build_exe(tmp_path)
     # unknown algorithm name -> VrCamException, exit code 3 (reference: throw VrCamException, CPU/PixFlow.hpp:499);
