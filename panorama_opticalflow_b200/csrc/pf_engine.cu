@@ -107,6 +107,8 @@ struct Workspace {
     float2* bufA[2] = {nullptr, nullptr};         // per direction: flow ping
     float2* bufB[2] = {nullptr, nullptr};         // flow pong
     float2* blurred[2] = {nullptr, nullptr};
+    // TMA tile maps of the flow buffers, per direction and level: blur box on bufA, median box on bufA and on bufB
+    std::vector<pf::FlowTileMap> tmBlurA[2], tmMedA[2], tmMedB[2];
     float* ratio[2] = {nullptr, nullptr};
     uint4* bnd[2] = {nullptr, nullptr};
     int* tickets[2] = {nullptr, nullptr};
@@ -158,6 +160,7 @@ struct Workspace {
         plan.build(rows, cols, pad);
         const Plan& p = plan;
         const size_t px0 = (size_t)p.dw * p.dh;
+        const size_t fpx0 = (size_t)pf::flow_pitch(p.dw) * p.dh;       // pitched flow buffers (every level fits: pitch and rows shrink together)
         for (int k = 0; k < 2; ++k) {
             PF_CUDA(cudaMalloc(&in[k], (size_t)rows * cols * 4));
             PF_CUDA(cudaMalloc(&I[k], p.total_px * sizeof(float)));
@@ -165,9 +168,16 @@ struct Workspace {
             PF_CUDA(cudaMalloc(&G[k], p.total_px * sizeof(float2)));
             PF_CUDA(cudaMalloc(&Gs[k], p.skew_total * sizeof(float2)));
             PF_CUDA(cudaMalloc(&rec[k], pf::sweep_rec_count(p.dh, p.dw) * sizeof(pf::SweepRec)));
-            PF_CUDA(cudaMalloc(&bufA[k], px0 * sizeof(float2)));
-            PF_CUDA(cudaMalloc(&bufB[k], px0 * sizeof(float2)));
-            PF_CUDA(cudaMalloc(&blurred[k], px0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&bufA[k], fpx0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&bufB[k], fpx0 * sizeof(float2)));
+            PF_CUDA(cudaMalloc(&blurred[k], fpx0 * sizeof(float2)));
+            tmBlurA[k].resize(p.L); tmMedA[k].resize(p.L); tmMedB[k].resize(p.L);
+            for (int l = 0; l < p.L; ++l) {
+                const int fp = pf::flow_pitch(p.ws[l]);
+                pf::make_blur_tile_map(&tmBlurA[k][l], bufA[k], p.hs[l], p.ws[l], fp);
+                pf::make_median_tile_map(&tmMedA[k][l], bufA[k], p.hs[l], p.ws[l], fp);
+                pf::make_median_tile_map(&tmMedB[k][l], bufB[k], p.hs[l], p.ws[l], fp);
+            }
             PF_CUDA(cudaMalloc(&ratio[k], 256));
             PF_CUDA(cudaMalloc(&bnd[k], (p.bnd_lines + 1) * sizeof(uint4)));
             PF_CUDA(cudaMalloc(&tickets[k], (size_t)p.L * 2 * sizeof(int)));
@@ -307,13 +317,13 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
     float2* flow = w.bufA[d];
     float2* other = w.bufB[d];
     for (int l = p.L - 1; l >= 0; --l) {
-        const int h = p.hs[l], wd = p.ws[l];
+        const int h = p.hs[l], wd = p.ws[l], fp = pf::flow_pitch(wd);
         const float* I0 = w.I[i0] + p.off[l];
         const float* I1 = w.I[i1] + p.off[l];
         const float* A0 = w.A[i0] + p.off[l];
         const float* A1 = w.A[i1] + p.off[l];
         if (l == p.L - 1) {
-            pf::launch_initial_flow(I0, I1, A0, A1, flow, w.ratio[d], h, wd, hint, e->search_dist, st);
+            pf::launch_initial_flow(I0, I1, A0, A1, flow, fp, w.ratio[d], h, wd, hint, e->search_dist, st);
             LAUNCHED(e->search_dist > 0 && hint != PF_HINT_UNKNOWN ? 2 : 1);
         }
         const float2* G0 = w.G[i0] + p.off[l];
@@ -324,16 +334,17 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
         sa.s = p.skew[l];
         sa.g1s_last = (long long)pf::skew_elems(p.skew[l]) - 1;
         // blur of the incoming flow (the sweeps regularise against it) + records of the forward sweep
-        pf::launch_blur15_prep(flow, w.blurred[d], h, wd, A0, A1, G0, G1, w.rec[d], +1, st);
+        pf::launch_blur15_prep(flow, w.blurred[d], h, wd, fp, A0, A1, G0, G1, w.rec[d], +1, &w.tmBlurA[d][l], st);
         // forward sweep, in place on `flow`
         sa.flow = flow;
+        sa.fp = fp;
         sa.boundary = w.bnd[d] + p.bnd_off[2 * l];
         sa.ticket = w.tickets[d] + 2 * l;
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
         pf::launch_sweep2(sa, +1, st);
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
         // median + records of the backward sweep
-        pf::launch_median5_prep(flow, other, w.blurred[d], h, wd, A0, A1, G0, G1, w.rec[d], -1, st);
+        pf::launch_median5_prep(flow, other, w.blurred[d], h, wd, fp, A0, A1, G0, G1, w.rec[d], -1, &w.tmMedA[d][l], st);
         // backward sweep, in place on `other`
         sa.flow = other;
         sa.boundary = w.bnd[d] + p.bnd_off[2 * l + 1];
@@ -341,15 +352,15 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
         pf::launch_sweep2(sa, -1, st);
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
-        pf::launch_median5(other, flow, h, wd, st);
+        pf::launch_median5(other, flow, h, wd, fp, &w.tmMedB[d][l], st);
         // lowAlphaFlowDiffusion: blur + blend, written to `other`
-        pf::launch_blur15_diffuse(flow, other, h, wd, A0, A1, st);
+        pf::launch_blur15_diffuse(flow, other, h, wd, fp, A0, A1, &w.tmBlurA[d][l], st);
         LAUNCHED(6);
         if (l > 0) {
-            pf::launch_upsample_cubic(other, h, wd, flow, p.hs[l - 1], p.ws[l - 1], st);
+            pf::launch_upsample_cubic(other, h, wd, fp, flow, p.hs[l - 1], p.ws[l - 1], pf::flow_pitch(p.ws[l - 1]), st);
             LAUNCHED(1);
         } else {
-            pf::launch_tail(other, h, wd, p.rows, p.pcols, p.pad, p.cols, out, out_stride, st);
+            pf::launch_tail(other, h, wd, fp, p.rows, p.pcols, p.pad, p.cols, out, out_stride, st);
             LAUNCHED(1);
         }
     }
@@ -1168,11 +1179,13 @@ int pf_stage_blur15(const float* flow, float* dst, int h, int w, const float* al
     DevBuf s, d, a0, a1;
     const size_t n = (size_t)h * w * 8;
     RC(s.upload(flow, n)); RC(d.alloc(n));
+    pf::FlowTileMap tm;                      // dense rows: describable when w is even (row bytes a multiple of 16)
+    pf::make_blur_tile_map(&tm, s.as<float2>(), h, w, w);
     if (alpha0) {
         RC(a0.upload(alpha0, n / 2)); RC(a1.upload(alpha1, n / 2));
-        pf::launch_blur15_diffuse(s.as<float2>(), d.as<float2>(), h, w, a0.as<float>(), a1.as<float>(), 0);
+        pf::launch_blur15_diffuse(s.as<float2>(), d.as<float2>(), h, w, w, a0.as<float>(), a1.as<float>(), &tm, 0);
     } else {
-        pf::launch_blur15(s.as<float2>(), d.as<float2>(), h, w, 0);
+        pf::launch_blur15(s.as<float2>(), d.as<float2>(), h, w, w, &tm, 0);
     }
     LAUNCHED(1);
     return d.download(dst, n);
@@ -1181,7 +1194,9 @@ int pf_stage_median5(const float* flow, float* dst, int h, int w) {
     DevBuf s, d;
     const size_t n = (size_t)h * w * 8;
     RC(s.upload(flow, n)); RC(d.alloc(n));
-    pf::launch_median5(s.as<float2>(), d.as<float2>(), h, w, 0);
+    pf::FlowTileMap tm;
+    pf::make_median_tile_map(&tm, s.as<float2>(), h, w, w);
+    pf::launch_median5(s.as<float2>(), d.as<float2>(), h, w, w, &tm, 0);
     LAUNCHED(1);
     return d.download(dst, n);
 }
@@ -1198,10 +1213,10 @@ int pf_stage_sweep(const float* alpha0, const float* alpha1, const float* G0, co
     RC(bnd.alloc(lines * 16)); RC(tk.alloc(16));
     PF_CUDA(cudaMemset(bnd.p, 0, lines * 16)); PF_CUDA(cudaMemset(tk.p, 0, 16));
     pf::launch_skew_copy_f2(g1.as<float2>(), g1s.as<float2>(), sk, 0);
-    pf::launch_sweep_prep(a0.as<float>(), a1.as<float>(), g0.as<float2>(), g1.as<float2>(), bl.as<float2>(), f.as<float2>(),
+    pf::launch_sweep_prep(a0.as<float>(), a1.as<float>(), g0.as<float2>(), g1.as<float2>(), bl.as<float2>(), f.as<float2>(), w,
                           ra.as<pf::SweepRec>(), h, w, dir, 0);
     pf::Sweep2Args sa;
-    sa.rec = ra.as<pf::SweepRec>(); sa.G1s = g1s.as<float2>(); sa.flow = f.as<float2>();
+    sa.rec = ra.as<pf::SweepRec>(); sa.G1s = g1s.as<float2>(); sa.flow = f.as<float2>(); sa.fp = w;
     sa.s = sk; sa.g1s_last = (long long)ne - 1; sa.boundary = bnd.as<uint4>(); sa.ticket = tk.as<int>();
     pf::launch_sweep2(sa, dir, 0);
     LAUNCHED(3);
@@ -1210,14 +1225,14 @@ int pf_stage_sweep(const float* alpha0, const float* alpha1, const float* G0, co
 int pf_stage_upsample_cubic(const float* src, int sh, int sw, float* dst, int dh, int dw) {
     DevBuf s, d;
     RC(s.upload(src, (size_t)sh * sw * 8)); RC(d.alloc((size_t)dh * dw * 8));
-    pf::launch_upsample_cubic(s.as<float2>(), sh, sw, d.as<float2>(), dh, dw, 0);
+    pf::launch_upsample_cubic(s.as<float2>(), sh, sw, sw, d.as<float2>(), dh, dw, dw, 0);
     LAUNCHED(1);
     return d.download(dst, (size_t)dh * dw * 8);
 }
 int pf_stage_tail(const float* flow0, int sh, int sw, int rows, int pcols, int pad, int cols, float* out) {
     DevBuf s, d;
     RC(s.upload(flow0, (size_t)sh * sw * 8)); RC(d.alloc((size_t)rows * cols * 8));
-    pf::launch_tail(s.as<float2>(), sh, sw, rows, pcols, pad, cols, d.as<float2>(), (size_t)cols * 8, 0);
+    pf::launch_tail(s.as<float2>(), sh, sw, sw, rows, pcols, pad, cols, d.as<float2>(), (size_t)cols * 8, 0);
     LAUNCHED(1);
     return d.download(out, (size_t)rows * cols * 8);
 }
@@ -1227,7 +1242,7 @@ int pf_stage_initial_flow(const float* I0, const float* I1, const float* alpha0,
     const size_t n = (size_t)h * w;
     RC(i0.upload(I0, n * 4)); RC(i1.upload(I1, n * 4)); RC(a0.upload(alpha0, n * 4)); RC(a1.upload(alpha1, n * 4));
     RC(f.alloc(n * 8)); RC(r.alloc(16));
-    pf::launch_initial_flow(i0.as<float>(), i1.as<float>(), a0.as<float>(), a1.as<float>(), f.as<float2>(), r.as<float>(), h, w, hint, dist, 0);
+    pf::launch_initial_flow(i0.as<float>(), i1.as<float>(), a0.as<float>(), a1.as<float>(), f.as<float2>(), w, r.as<float>(), h, w, hint, dist, 0);
     LAUNCHED(2);
     return f.download(flow, n * 8);
 }

@@ -240,7 +240,7 @@ void launch_gradient(const float* I, float2* G, int h, int w, cudaStream_t st) {
 // inter-level upsample: INTER_CUBIC on float2, then * (1/0.9)
 // ====================================================================================================
 __global__ void __launch_bounds__(256)
-k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, float2* __restrict__ dst, int dh, int dw,
+k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, int sp, float2* __restrict__ dst, int dh, int dw, int dp,
                  double scale_x, double scale_y) {
     __shared__ int s_sx[32], s_sy[8];
     __shared__ float s_ca[32][4], s_cb[8][4];
@@ -273,7 +273,7 @@ k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, float2* __restr
     f2p r[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const f2p* S = reinterpret_cast<const f2p*>(src + clampi(sy - 1 + k, 0, sh - 1) * sw);
+        const f2p* S = reinterpret_cast<const f2p*>(src + clampi(sy - 1 + k, 0, sh - 1) * sp);
         r[k] = padd(padd(padd(pmuls(S[xs[0]], ca[0]), pmuls(S[xs[1]], ca[1])), pmuls(S[xs[2]], ca[2])), pmuls(S[xs[3]], ca[3]));
     }
     // vertical pass: right-to-left for the first n - n%4 floats of the row, left-to-right for the tail (n = 2*dw is even and
@@ -282,14 +282,14 @@ k_upsample_cubic(const float2* __restrict__ src, int sh, int sw, float2* __restr
     f2p o;
     if (2 * x < nv) o = padd(padd(padd(pmuls(r[3], cb[3]), pmuls(r[2], cb[2])), pmuls(r[1], cb[1])), pmuls(r[0], cb[0]));
     else            o = padd(padd(padd(pmuls(r[0], cb[0]), pmuls(r[1], cb[1])), pmuls(r[2], cb[2])), pmuls(r[3], cb[3]));
-    dst[y * dw + x] = upk(pmuls(o, PF_INV_PYR));
+    dst[y * dp + x] = upk(pmuls(o, PF_INV_PYR));
 }
 
-void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int dh, int dw, cudaStream_t st) {
+void launch_upsample_cubic(const float2* src, int sh, int sw, int sp, float2* dst, int dh, int dw, int dp, cudaStream_t st) {
     const double scale_x = 1.0 / ((double)dw / (double)sw);
     const double scale_y = 1.0 / ((double)dh / (double)sh);
     dim3 b(32, 8);
-    k_upsample_cubic<<<grid2d(dw, dh, b), b, 0, st>>>(src, sh, sw, dst, dh, dw, scale_x, scale_y);
+    k_upsample_cubic<<<grid2d(dw, dh, b), b, 0, st>>>(src, sh, sw, sp, dst, dh, dw, dp, scale_x, scale_y);
 }
 
 // ====================================================================================================
@@ -299,7 +299,7 @@ void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int d
 // halo into shared memory (reflect-101 of the 3x3 blur applied to the coordinates of the padded full-size image), then
 // the 3x3 sigma-1 row and column passes run from shared memory.
 __global__ void __launch_bounds__(256)
-k_tail(const float2* __restrict__ src, int sh, int sw, int rows, int pcols, int pad, int cols,
+k_tail(const float2* __restrict__ src, int sh, int sw, int sp, int rows, int pcols, int pad, int cols,
        float2* __restrict__ out, size_t out_stride, double scale_x, double scale_y) {
     PF_GAUSS_TABLES
     __shared__ int s_xs[34];
@@ -328,8 +328,8 @@ k_tail(const float2* __restrict__ src, int sh, int sw, int rows, int pcols, int 
     const f2p* srcp = reinterpret_cast<const f2p*>(src);
     for (int e = tid; e < 10 * 34; e += 256) {
         const int ly = e / 34, lx = e - ly * 34;
-        const f2p* S0 = srcp + s_y0[ly] * sw;
-        const f2p* S1 = srcp + s_y1[ly] * sw;
+        const f2p* S0 = srcp + s_y0[ly] * sp;
+        const f2p* S1 = srcp + s_y1[ly] * sp;
         const int s = s_xs[lx];
         const float b1 = s_fy[ly], b0 = fsub(1.0f, b1);
         f2p r0, r1;
@@ -354,12 +354,12 @@ k_tail(const float2* __restrict__ src, int sh, int sw, int rows, int pcols, int 
     (void)kG5; (void)kG3H; (void)kG15;
 }
 
-void launch_tail(const float2* flow0, int sh, int sw, int rows, int pcols, int pad, int cols,
+void launch_tail(const float2* flow0, int sh, int sw, int sp, int rows, int pcols, int pad, int cols,
                  float2* out, size_t out_stride, cudaStream_t st) {
     const double scale_x = 1.0 / ((double)pcols / (double)sw);
     const double scale_y = 1.0 / ((double)rows / (double)sh);
     dim3 b(32, 8);
-    k_tail<<<grid2d(cols, rows, b), b, 0, st>>>(flow0, sh, sw, rows, pcols, pad, cols, out, out_stride, scale_x, scale_y);
+    k_tail<<<grid2d(cols, rows, b), b, 0, st>>>(flow0, sh, sw, sp, rows, pcols, pad, cols, out, out_stride, scale_x, scale_y);
 }
 
 // ====================================================================================================
@@ -408,7 +408,7 @@ __device__ float patch_error(const float* __restrict__ i0, const float* __restri
 __global__ void __launch_bounds__(128)
 k_adjust_initial_flow(const float* __restrict__ I0, const float* __restrict__ I1,
                       const float* __restrict__ a0, const float* __restrict__ a1, float2* __restrict__ flow,
-                      const float* __restrict__ ratio_p, int h, int w, int bx, int by, int bw, int bh, int dist) {
+                      const float* __restrict__ ratio_p, int h, int w, int fp, int bx, int by, int bw, int bh, int dist) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
@@ -427,11 +427,11 @@ k_adjust_initial_flow(const float* __restrict__ I0, const float* __restrict__ I1
             }
         out = make_float2((float)(bestx - x), (float)(besty - y));
     }
-    flow[(size_t)y * w + x] = out;
+    flow[(size_t)y * fp + x] = out;
 }
 
 void launch_initial_flow(const float* I0, const float* I1, const float* alpha0, const float* alpha1,
-                         float2* flow, float* ratio, int h, int w, int hint, int dist, cudaStream_t st) {
+                         float2* flow, int fp, float* ratio, int h, int w, int hint, int dist, cudaStream_t st) {
     int bx = 0, by = 0, bw = 0, bh = 0;
     if (dist > 0 && hint >= 1 && hint <= 4) {   // computeSearchBox, CPU/PixFlow.hpp:207-224
         const int ortho = (dist + 8 / 2) / 8, thick = 2 * ortho + 1;
@@ -444,7 +444,7 @@ void launch_initial_flow(const float* I0, const float* I1, const float* alpha0, 
         k_intensity_ratio<<<1, 32, 0, st>>>(I0, alpha0, I1, alpha1, h * w, ratio);
     }
     dim3 b(32, 4);
-    k_adjust_initial_flow<<<grid2d(w, h, b), b, 0, st>>>(I0, I1, alpha0, alpha1, flow, ratio, h, w, bx, by, bw, bh, dist);
+    k_adjust_initial_flow<<<grid2d(w, h, b), b, 0, st>>>(I0, I1, alpha0, alpha1, flow, ratio, h, w, fp, bx, by, bw, bh, dist);
 }
 
 // ====================================================================================================

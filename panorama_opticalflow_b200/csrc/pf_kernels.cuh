@@ -37,24 +37,36 @@ constexpr int SWEEP_GROUP_ROWS = 16;      // logical rows per sweep warp (two la
 int sweep_nsteps_pad(int w);              // wavefront steps of a row group, rounded up to whole TMA stages
 size_t sweep_rec_count(int h, int w);     // SweepRec elements a (h x w) level needs
 void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
-                       const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st);
+                       const float2* blurred, const float2* flow, int fp, SweepRec* rec, int h, int w, int dir, cudaStream_t st);
 
 // ---- fused, shared-memory-tiled stencils of one level (pf_fused.cu) -----------------------------------------------
 // 15x15 sigma 8 blur of the 2-channel flow (CPU/PixFlow.hpp:307): plain, with the forward sweep's records fused in,
 // or with lowAlphaFlowDiffusion (CPU/PixFlow.hpp:388-405) fused in
-void launch_blur15(const float2* flow, float2* blurred, int h, int w, cudaStream_t st);
-void launch_blur15_prep(const float2* flow, float2* blurred, int h, int w, const float* alpha0, const float* alpha1,
-                        const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st);
-void launch_blur15_diffuse(const float2* flow, float2* out, int h, int w, const float* alpha0, const float* alpha1, cudaStream_t st);
+// The flow buffers (flow ping / pong, blurred flow) are row-major float2 with a row pitch of flow_pitch(w) elements -- a multiple
+// of 16 bytes, which is what a TMA tensor map needs.  FlowTileMap: a CUtensorMap (opaque here, so that this header needs no
+// <cuda.h>) describing one such buffer at one level for the tile + halo box of the blur (46 x 46) or of the median (36 x 12);
+// valid == 0 (layout not describable, or maps unavailable) makes the kernels use per-thread loads for every tile.
+int flow_pitch(int w);
+struct alignas(64) FlowTileMap { unsigned char opaque[128]; int valid; };
+bool make_blur_tile_map(FlowTileMap* out, const float2* base, int h, int w, int fp);
+bool make_median_tile_map(FlowTileMap* out, const float2* base, int h, int w, int fp);
+// fp: row pitch (elements) of the flow buffers involved; tm: tile map of the INPUT buffer (may be NULL)
+void launch_blur15(const float2* flow, float2* blurred, int h, int w, int fp, const FlowTileMap* tm, cudaStream_t st);
+void launch_blur15_prep(const float2* flow, float2* blurred, int h, int w, int fp, const float* alpha0, const float* alpha1,
+                        const float2* G0, const float2* G1, SweepRec* rec, int dir, const FlowTileMap* tm, cudaStream_t st);
+void launch_blur15_diffuse(const float2* flow, float2* out, int h, int w, int fp, const float* alpha0, const float* alpha1,
+                           const FlowTileMap* tm, cudaStream_t st);
 // medianBlur(32FC2, 5) (CPU/PixFlow.hpp:325, :338): plain, or with the backward sweep's records fused in
-void launch_median5(const float2* src, float2* dst, int h, int w, cudaStream_t st);
-void launch_median5_prep(const float2* src, float2* dst, const float2* blurred, int h, int w, const float* alpha0,
-                         const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir, cudaStream_t st);
+void launch_median5(const float2* src, float2* dst, int h, int w, int fp, const FlowTileMap* tm, cudaStream_t st);
+void launch_median5_prep(const float2* src, float2* dst, const float2* blurred, int h, int w, int fp, const float* alpha0,
+                         const float* alpha1, const float2* G0, const float2* G1, SweepRec* rec, int dir, const FlowTileMap* tm,
+                         cudaStream_t st);
 struct Sweep2Args {
     const SweepRec* rec;                      // wavefront-packed records from launch_sweep_prep (same dir)
     const float2* G1s;                        // skewed gradients of image 1
     long long g1s_last;                       // index of the last element of G1s (prefetch clamp)
-    float2* flow;                             // row-major, updated in place where alpha > 0.9
+    float2* flow;                             // row-major with row pitch fp, updated in place where alpha > 0.9
+    int fp;                                   // row pitch of flow, in elements
     Skew s;
     uint4* boundary;      // LL lines {fx, flag, fy, flag}, zero-initialised (sweep2_boundary_lines of them)
     int* ticket;          // zero-initialised block ticket counter
@@ -63,17 +75,18 @@ size_t sweep2_boundary_lines(int h, int w);
 void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st);
 
 // ---- inter-level upsample (CPU/PixFlow.hpp:123-124): INTER_CUBIC 32FC2 + "*= 1/0.9" --------------------
-void launch_upsample_cubic(const float2* src, int sh, int sw, float2* dst, int dh, int dw, cudaStream_t st);
+// sp / dp: row pitch (elements) of the source / destination flow buffer
+void launch_upsample_cubic(const float2* src, int sh, int sw, int sp, float2* dst, int dh, int dw, int dp, cudaStream_t st);
 
 // ---- tail (CPU/PixFlow.hpp:128-134): INTER_LINEAR to (rows x pcols), *2, 3x3 sigma 1 blur; only columns
 // [pad, pad+cols) are written (the crop of CPU/OpticalFlow.cpp:143-144), out_stride in bytes -------------
-void launch_tail(const float2* flow0, int sh, int sw, int rows, int pcols, int pad, int cols,
+void launch_tail(const float2* flow0, int sh, int sw, int sp, int rows, int pcols, int pad, int cols,
                  float2* out, size_t out_stride, cudaStream_t st);
 
 // ---- coarsest-level search (CPU/PixFlow.hpp:190-270) ---------------------------------------------------
 // ratio[0] <- computeIntensityRatio; flow <- zeros + adjustInitialFlow (hint 1..4, dist > 0) or zeros
 void launch_initial_flow(const float* I0, const float* I1, const float* alpha0, const float* alpha1,
-                         float2* flow, float* ratio, int h, int w, int hint, int dist, cudaStream_t st);
+                         float2* flow, int fp, float* ratio, int h, int w, int hint, int dist, cudaStream_t st);
 
 // ---- combineNovelViews (CPU/OpticalFlow.cpp:9-92); strides in bytes -------------------------------------
 void launch_combine(const uint8_t* imageL, size_t strideL, const uint8_t* imageR, size_t strideR,

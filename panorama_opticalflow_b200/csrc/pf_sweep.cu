@@ -120,12 +120,12 @@ size_t sweep_rec_count(int h, int w) {
 
 // stand-alone form (the production path fuses this into the blur / median kernels, pf_fused.cu)
 __global__ void __launch_bounds__(256)
-k_sweep_prep(const float2* __restrict__ blurred, const float2* __restrict__ flow, int h, int w, PrepArgs pa) {
+k_sweep_prep(const float2* __restrict__ blurred, const float2* __restrict__ flow, int fp, int h, int w, PrepArgs pa) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
     const ErrCtx c = make_err_ctx(pa.G1, w, h);
-    const size_t p = (size_t)y * w + x;
+    const size_t p = (size_t)y * fp + x;
     emit_record(pa, c, x, y, w, h, flow[p], blurred[p]);
 }
 
@@ -139,9 +139,9 @@ PrepArgs make_prep_args(const float* alpha0, const float* alpha1, const float2* 
 }
 
 void launch_sweep_prep(const float* alpha0, const float* alpha1, const float2* G0, const float2* G1,
-                       const float2* blurred, const float2* flow, SweepRec* rec, int h, int w, int dir, cudaStream_t st) {
+                       const float2* blurred, const float2* flow, int fp, SweepRec* rec, int h, int w, int dir, cudaStream_t st) {
     dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
-    k_sweep_prep<<<g, b, 0, st>>>(blurred, flow, h, w, make_prep_args(alpha0, alpha1, G0, G1, rec, w, dir));
+    k_sweep_prep<<<g, b, 0, st>>>(blurred, flow, fp, h, w, make_prep_args(alpha0, alpha1, G0, G1, rec, w, dir));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -437,7 +437,7 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
     const float yf = pin_f((float)y);
     float xf = (float)(DIR > 0 ? -g : w - 1 + g);                  // float(x) of step 0, then +-1 per step (exact)
     int i = rowValid ? -g : -0x40000000;                           // logical column of this row, +1 per step; rows past h never become valid
-    float2* fptr = a.flow + (size_t)y * w + (DIR > 0 ? -g : w - 1 + g);          // &flow(y, x) of the current step (dereferenced only where valid)
+    float2* fptr = a.flow + (size_t)y * a.fp + (DIR > 0 ? -g : w - 1 + g);          // &flow(y, x) of the current step (dereferenced only where valid)
     uint4* gptr = a.boundary + (size_t)b * w - (SW_ROWS - 1);      // &boundary line of the last row's column (i_last = s - 15)
 
     // ---- record stream: 512 bytes per step, 4 steps per TMA bulk copy, SW_NSTAGES stages, fed by this warp's lane 0 ----

@@ -60,7 +60,8 @@ def test_gradient(orc, shape):
     assert_bit_equal(stages.gradient(a), _grad(orc, a), "gradient")
 
 
-@pytest.mark.parametrize("shape", [(26, 25), (45, 61), (130, 99)])
+# even widths >= 46 make interior tiles go through the TMA tensor copy, odd widths / small images through per-thread loads
+@pytest.mark.parametrize("shape", [(26, 25), (45, 61), (130, 99), (150, 200), (97, 46), (46, 160)])
 def test_blur15_and_diffusion(orc, shape):
     from panorama_opticalflow_b200 import stages
     f = (RNG.standard_normal(shape + (2,)) * 3).astype(np.float32)
@@ -70,7 +71,7 @@ def test_blur15_and_diffusion(orc, shape):
     assert_bit_equal(stages.blur15(f, a0, a1), orc.low_alpha_diffusion(a0, a1, f), "diffusion")
 
 
-@pytest.mark.parametrize("shape", [(25, 26), (37, 45), (120, 131)])
+@pytest.mark.parametrize("shape", [(25, 26), (37, 45), (120, 131), (64, 200), (12, 36), (99, 130)])
 def test_median5(orc, shape):
     from panorama_opticalflow_b200 import stages
     f = RNG.standard_normal(shape + (2,)).astype(np.float32)
