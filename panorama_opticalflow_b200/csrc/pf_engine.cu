@@ -128,7 +128,8 @@ struct Workspace {
     // with a single launch: ~1000 kernel launches per pair would otherwise cost ~3 ms of host time each call
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_launches = 0;                  // kernels per replay
-    int graph_key = -1;                           // ndir | hint0 << 4 | hint1 << 8 | search_dist << 12
+    int graph_key = -1;                           // ndir | hint0 << 4 | hint1 << 8 | search_dist << 12 | sweep_cta_divisor << 20
+    int sweep_cta_divisor = 1;                    // for the next enqueue: 1 latency flavour, > 1 throughput flavour (launch_sweep2)
 
     ~Workspace() { release(); }
     void release() {
@@ -338,6 +339,7 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
         // forward sweep, in place on `flow`
         sa.flow = flow;
         sa.fp = fp;
+        sa.cta_divisor = w.sweep_cta_divisor;
         sa.boundary = w.bnd[d] + p.bnd_off[2 * l];
         sa.ticket = w.tickets[d] + 2 * l;
         if (e->time_sweeps) cudaEventRecord(next_sweep_event(w, d), st);
@@ -429,7 +431,7 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
             PF_CUDA(cudaEventRecord(w.evIn, e->sCopy));
             PF_CUDA(cudaStreamWaitEvent(st, w.evIn, 0));
         }
-        const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12);
+        const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12) | (w.sweep_cta_divisor << 20);
         bool have_graph = w.graph_key == key;
         if (!have_graph) {
             std::lock_guard<std::mutex> cg(g_capture_mu);
@@ -652,6 +654,7 @@ int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, siz
     Workspace* w;
     if ((rc = wait_slot_locked(e, 0)) != PF_OK) return rc;        // an asynchronous batch may still own workspace 0
     if ((rc = e->workspace(0, rows, cols, 0, &w)) != PF_OK) return rc;
+    w->sweep_cta_divisor = 1;
     const int hints[2] = {hint, 0};
     void* outs[2] = {flow_out, nullptr};
     const size_t ostr[2] = {flow_stride, 0};
@@ -660,6 +663,21 @@ int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, siz
     if ((rc = sync_pair(*w, 1)) != PF_OK) return rc;
     std::vector<Workspace*> used{w};
     return collect_sweep_timing(e, used);
+}
+
+// Sweep launch flavour for n pairs in flight on the device: alone (or nearly), a pair waits for its wavefronts' dependent chains ->
+// full front of CTAs; with many pairs in flight SM slots are the scarce resource -> a fraction of the front (launch_sweep2).
+// PF_SWEEP_CTA_DIVISOR sets the throughput flavour's divisor (default 1 = off: measured 1247 / 1246 / 1118 / 993 Mpix/s for 1 / 2 / 3 / 4), PF_LATENCY_MAX_PAIRS the switch-over (default 2).
+static int sweep_cta_divisor_for_pairs(int n) {
+    static int max_pairs = -1, div = 2;
+    if (max_pairs < 0) {
+        const char* a = getenv("PF_LATENCY_MAX_PAIRS");
+        const char* b = getenv("PF_SWEEP_CTA_DIVISOR");
+        max_pairs = a ? atoi(a) : 2;
+        div = b ? atoi(b) : 1;
+        if (div < 1 || div > 16) div = 1;
+    }
+    return n <= max_pairs ? 1 : div;
 }
 
 // workspace index of pair i of slot s: the two slots own disjoint workspaces (streams, graphs, staging and output buffers)
@@ -686,6 +704,7 @@ static int batch_enqueue_locked(pf_engine* e, int slot, int n, const void* const
         Workspace* w;
         if ((rc = e->workspace(ws_index(slot, i), rows, cols, pad, &w)) != PF_OK) return rc;
         e->inflight[slot].push_back(w);
+        w->sweep_cta_divisor = sweep_cta_divisor_for_pairs(n);
         void* outs[2] = {lr[i], rl[i]};
         const size_t ostr[2] = {slr, srl};
         const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
@@ -830,6 +849,7 @@ static int novel_view_locked(pf_engine* e, const void* L, size_t sl, const void*
     const int pad = cols / 20;
     if ((rc = wait_slot_locked(e, 0)) != PF_OK) return rc;
     if ((rc = e->workspace(0, rows, cols, pad, &w)) != PF_OK) return rc;
+    w->sweep_cta_divisor = 1;
     w->preWait = inputs_ready;
     const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};
     void* outs[2] = {lr, rl};
@@ -1217,7 +1237,7 @@ int pf_stage_sweep(const float* alpha0, const float* alpha1, const float* G0, co
                           ra.as<pf::SweepRec>(), h, w, dir, 0);
     pf::Sweep2Args sa;
     sa.rec = ra.as<pf::SweepRec>(); sa.G1s = g1s.as<float2>(); sa.flow = f.as<float2>(); sa.fp = w;
-    sa.s = sk; sa.g1s_last = (long long)ne - 1; sa.boundary = bnd.as<uint4>(); sa.ticket = tk.as<int>();
+    sa.s = sk; sa.g1s_last = (long long)ne - 1; sa.boundary = bnd.as<uint4>(); sa.ticket = tk.as<int>(); sa.cta_divisor = 1;
     pf::launch_sweep2(sa, dir, 0);
     LAUNCHED(3);
     return f.download(flow, n * 8);

@@ -70,6 +70,7 @@ struct Sweep2Args {
     Skew s;
     uint4* boundary;      // LL lines {fx, flag, fy, flag}, zero-initialised (sweep2_boundary_lines of them)
     int* ticket;          // zero-initialised block ticket counter
+    int cta_divisor;      // 1: as many CTAs as row blocks overlap in time (shortest sweep); k > 1: 1/k of that (see launch_sweep2)
 };
 size_t sweep2_boundary_lines(int h, int w);
 void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st);

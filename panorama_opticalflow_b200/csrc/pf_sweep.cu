@@ -645,7 +645,12 @@ static int sweep_margin() {
 void launch_sweep2(const Sweep2Args& a, int dir, cudaStream_t st) {
     const int nblocks = (a.s.h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
     const int front = (a.s.w + 2 * SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA + sweep_margin();
-    const int ncta = nblocks < front ? nblocks : front;
+    int ncta = nblocks < front ? nblocks : front;
+    // Throughput flavour (many pairs in flight): CTA k of a launch cannot start before step k * SW_ROWS_PER_CTA, so a full front
+    // of persistent CTAs spends ~front^2 / 2 block-steps resident but idle while the pipeline fills -- SM slots that, with many
+    // wavefronts in flight, are what bounds the device.  A fraction of the front (each CTA then runs its row blocks back to back,
+    // never waiting for its upstream) makes one sweep longer and the device fuller.
+    if (a.cta_divisor > 1) ncta = (ncta + a.cta_divisor - 1) / a.cta_divisor;
     if (dir > 0) {
         if (a.s.posx) k_sweep<1, 1><<<ncta, SW_THREADS, 0, st>>>(a); else k_sweep<1, 0><<<ncta, SW_THREADS, 0, st>>>(a);
     } else {
