@@ -599,8 +599,11 @@ __device__ __forceinline__ void sweep_poller(const Sweep2Args& a, SweepSmem& sm,
 // that finishes its row block takes the next ticket.  Tickets are handed out in row-block order, so the block a CTA
 // waits on is always being processed (or done) -- no deadlock whatever the residency -- and CTAs far behind the
 // front do not occupy registers and shared memory while they would only be waiting for their turn.
+#ifndef PF_SWEEP_MIN_CTAS
+#define PF_SWEEP_MIN_CTAS 1
+#endif
 template <int DIR, int POSX>
-__global__ void __launch_bounds__(SW_THREADS)
+__global__ void __launch_bounds__(SW_THREADS, PF_SWEEP_MIN_CTAS)
 k_sweep(Sweep2Args a) {
     __shared__ SweepSmem sm;
     const int nblocks = (a.s.h + SW_ROWS_PER_CTA - 1) / SW_ROWS_PER_CTA;
