@@ -215,25 +215,25 @@ __device__ __forceinline__ f2p div2_by_const(f2p x, float d, float rd) {
     const f2p rem = pfma(q, pk(-d, -d), x);          // x - q*d, exact (FMA)
     return pfma(rem, pk(rd, rd), q);
 }
+// The seed is taken from max(a, 2^-126): for a == 0 the sequence then yields g = 0 * 2^63 = 0, r = 0, s = 0 (instead of 0 * inf),
+// with the sign of the zero preserved, so no select on a == 0 is needed; normal inputs are unaffected.
 __device__ __forceinline__ f2p sqrt2_exact_fast(float a0, float a1) {
     float y0, y1;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(a0));
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(a1));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(fmaxf(a0, 0x1p-126f)));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(fmaxf(a1, 0x1p-126f)));
     const f2p a = pk(a0, a1), y = pk(y0, y1);
     const f2p g = pmul(a, y), h = pmuls(y, 0.5f);
     const f2p r = pfma(pneg(g), g, a);
-    const float2 s = upk(pfma(r, h, g));
-    return pk(a0 == 0.0f ? a0 : s.x, a1 == 0.0f ? a1 : s.y);
+    return pfma(r, h, g);
 }
 
-// sqrt(a) for a in (2^-80, 2^80) or a == 0: rsqrt seed, one Newton step with exact residual
+// sqrt(a) for a in [2^-60, 2^126) or a == 0: rsqrt seed, one Newton step with exact residual
 __device__ __forceinline__ float sqrt_exact_fast(float a) {
     float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(a, 0x1p-126f)));
     const float g = __fmul_rn(a, y), h = __fmul_rn(y, 0.5f);
     const float r = __fmaf_rn(-g, g, a);
-    const float s = __fmaf_rn(r, h, g);
-    return a == 0.0f ? a : s;          // sqrt(+-0) = +-0
+    return __fmaf_rn(r, h, g);         // a == +-0: g = +-0, r = +-0, s = +-0
 }
 
 }  // namespace pf

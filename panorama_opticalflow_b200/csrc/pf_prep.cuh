@@ -57,32 +57,42 @@ __device__ __forceinline__ f2p bil_interp(const BilCoef& t, float xR, float yR) 
     return padd(padd(padd(t.f00, pmuls(t.a2, xR)), pmuls(t.a3, yR)), pmuls(pmuls(t.a4, xR), yR));
 }
 
-// errorFunction after the gather (CPU/PixFlow.hpp:447-455); `tiny` / `vmax` collect what the range check of the branch-free
-// exact sequences needs (see emit_record)
+// errorFunction after the gather (CPU/PixFlow.hpp:447-455) at the three probes (fx0, fy0), (fx1, fy0), (fx0, fy2) of one flow
+// vector -- E(f), E(f + (eps,0)), E(f + (0,eps)) of :318 / :382-383 -- given image 1's interpolated gradients G1a/b/c at the three
+// matched positions.  The probes share a component pairwise, so the smoothness squares and the two regularisers are computed for
+// the FOUR distinct components (two packed operations each) instead of six; every value is produced by the same fp32 operation
+// on the same operands as in the reference, so the sharing is exact.  (The reference adds 0.0f to the unchanged component of a
+// shifted probe; that only turns a -0 into +0, which none of |f|, (blur - f)^2 and the clamped match position can see.)
+// `tiny` collects what the range check of the branch-free exact sequences needs (see emit_record).
 template <bool SLOW>
-__device__ __forceinline__ float err_from_g1(const ErrCtx& c, float rcp_w, float2 g0, float2 bl, f2p g1, float fx, float fy, unsigned& tiny) {
-    const f2p D = psub(pk(bl), pk(fx, fy));
-    const float2 d2 = upk(pmul(D, D));
-    const float ss = fadd(d2.x, d2.y);
-    const f2p E = psub(pk(g0), g1);
-    const float2 e2 = upk(pmul(E, E));
-    const float gs = fadd(e2.x, e2.y);
-    const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
-    float smooth, grad, ry, rx;
+__device__ __forceinline__ void err3_from_g1(float fw, float rcp_w, float2 g0, float2 bl, f2p G1a, f2p G1b, f2p G1c,
+                                             float fx0, float fy0, float fx1, float fy2, float v[3], unsigned& tiny) {
+    const f2p BL = pk(bl), G0 = pk(g0);
+    const f2p Da = psub(BL, pk(fx0, fy0)), Db = psub(BL, pk(fx1, fy2));
+    const float2 qa = upk(pmul(Da, Da)), qb = upk(pmul(Db, Db));
+    const float ss0 = fadd(qa.x, qa.y), ss1 = fadd(qb.x, qa.y), ss2 = fadd(qa.x, qb.y);
+    const f2p Ea = psub(G0, G1a), Eb = psub(G0, G1b), Ec = psub(G0, G1c);
+    const float2 ea = upk(pmul(Ea, Ea)), eb = upk(pmul(Eb, Eb)), ec = upk(pmul(Ec, Ec));
+    const float gs0 = fadd(ea.x, ea.y), gs1 = fadd(eb.x, eb.y), gs2 = fadd(ec.x, ec.y);
+    const float ty0 = fmul(PF_VERT_REG_COEF, fabsf(fy0)), ty2 = fmul(PF_VERT_REG_COEF, fabsf(fy2));
+    const float tx0 = fmul(PF_HORZ_REG_COEF, fabsf(fx0)), tx1 = fmul(PF_HORZ_REG_COEF, fabsf(fx1));
+    float2 s0, s1, s2, ra, rb;       // {smoothness, gradient} norms per probe; {ry0, rx0}, {ry2, rx1}
     if (SLOW) {
-        smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
-        ry = __fdiv_rn(ty, c.fw); rx = __fdiv_rn(tx, c.fw);
+        s0 = make_float2(__fsqrt_rn(ss0), __fsqrt_rn(gs0));
+        s1 = make_float2(__fsqrt_rn(ss1), __fsqrt_rn(gs1));
+        s2 = make_float2(__fsqrt_rn(ss2), __fsqrt_rn(gs2));
+        ra = make_float2(__fdiv_rn(ty0, fw), __fdiv_rn(tx0, fw));
+        rb = make_float2(__fdiv_rn(ty2, fw), __fdiv_rn(tx1, fw));
     } else {
-        const float2 sq = upk(sqrt2_exact_fast(ss, gs));
-        smooth = sq.x; grad = sq.y;
-        const float2 rr = upk(div2_by_const(pk(ty, tx), c.fw, rcp_w));        // ty, tx >= +0
-        ry = rr.x; rx = rr.y;
-        tiny = min(tiny, min(min(tiny_key(ss), tiny_key(gs)), min(tiny_key(ty), tiny_key(tx))));
+        s0 = upk(sqrt2_exact_fast(ss0, gs0)); s1 = upk(sqrt2_exact_fast(ss1, gs1)); s2 = upk(sqrt2_exact_fast(ss2, gs2));
+        ra = upk(div2_by_const(pk(ty0, tx0), fw, rcp_w));                         // ty, tx >= +0
+        rb = upk(div2_by_const(pk(ty2, tx1), fw, rcp_w));
+        tiny = min(tiny, min(min(min(tiny_key(ss0), tiny_key(gs0)), min(tiny_key(ss1), tiny_key(gs1))), min(tiny_key(ss2), tiny_key(gs2))));
+        tiny = min(tiny, min(min(tiny_key(ty0), tiny_key(tx0)), min(tiny_key(ty2), tiny_key(tx1))));
     }
-    float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
-    err = fadd(err, ry);
-    err = fadd(err, rx);
-    return err;
+    v[0] = fadd(fadd(fadd(s0.y, fmul(s0.x, PF_SMOOTHNESS_COEF)), ra.x), ra.y);
+    v[1] = fadd(fadd(fadd(s1.y, fmul(s1.x, PF_SMOOTHNESS_COEF)), ra.x), rb.y);
+    v[2] = fadd(fadd(fadd(s2.y, fmul(s2.x, PF_SMOOTHNESS_COEF)), rb.x), ra.y);
 }
 
 // Record {E(f0), r0.x, r0.y, - | I0x, I0y, blur.x, blur.y} of pixel (x,y) with old flow f and blurred flow bl
@@ -95,20 +105,20 @@ __device__ __forceinline__ void emit_record(const PrepArgs& a, const ErrCtx& c, 
     float4 A = make_float4(__int_as_float(0xff800000), f.x, f.y, 0.0f);
     if (a.alpha0[p] > PF_ALPHA_THRESHOLD && a.alpha1[p] > PF_ALPHA_THRESHOLD) {
         const float xf = (float)x, yf = (float)y;
-        const float fx1 = fadd(f.x, PF_GRAD_EPS), fy1 = fadd(f.y, 0.0f);
-        const float fx2 = fadd(f.x, 0.0f), fy2 = fadd(f.y, PF_GRAD_EPS);
+        // (the reference's f.y + 0.0f / f.x + 0.0f of the shifted probes is dropped: see err3_from_g1)
+        const float fx1 = fadd(f.x, PF_GRAD_EPS), fy2 = fadd(f.y, PF_GRAD_EPS);
         const BilCell c0 = bil_cell_rm(c, fadd(xf, f.x), fadd(yf, f.y));
-        const BilCell c1 = bil_cell_rm(c, fadd(xf, fx1), fadd(yf, fy1));
-        const BilCell c2 = bil_cell_rm(c, fadd(xf, fx2), fadd(yf, fy2));
+        const BilCell c1 = bil_cell_rm(c, fadd(xf, fx1), fadd(yf, f.y));
+        const BilCell c2 = bil_cell_rm(c, fadd(xf, f.x), fadd(yf, fy2));
         // every probe gathers its own bilinear cell (no divergent re-gather when a probe crosses a cell boundary, which is common:
         // gradient descent parks many pixels within eps of one)
         const BilCoef t0 = load_coef_rm(c, c0.x0, c0.y0), t1 = load_coef_rm(c, c1.x0, c1.y0), t2 = load_coef_rm(c, c2.x0, c2.y0);
         const f2p g1a = bil_interp(t0, c0.xR, c0.yR), g1b = bil_interp(t1, c1.xR, c1.yR), g1c = bil_interp(t2, c2.xR, c2.yR);
         const float rcp_w = __frcp_rn(c.fw), rcp_eps = __frcp_rn(PF_GRAD_EPS);
         unsigned tiny = 0xffffffffu;
-        float e0 = err_from_g1<false>(c, rcp_w, g0, bl, g1a, f.x, f.y, tiny);
-        float ex = err_from_g1<false>(c, rcp_w, g0, bl, g1b, fx1, fy1, tiny);
-        float ey = err_from_g1<false>(c, rcp_w, g0, bl, g1c, fx2, fy2, tiny);
+        float ev[3];
+        err3_from_g1<false>(c.fw, rcp_w, g0, bl, g1a, g1b, g1c, f.x, f.y, fx1, fy2, ev, tiny);
+        float e0 = ev[0], ex = ev[1], ey = ev[2];
         const float2 d = upk(psub(pk(ex, ey), pk(e0, e0)));
         float2 q = upk(div2_by_const(pk(d.x, d.y), PF_GRAD_EPS, rcp_eps));            // a difference of errors is never -0
         tiny = min(tiny, min(tiny_key(fabsf(d.x)), tiny_key(fabsf(d.y))));
@@ -118,9 +128,8 @@ __device__ __forceinline__ void emit_record(const PrepArgs& a, const ErrCtx& c, 
         const bool bad = a.slow || (tiny < PF_TINY_BITS - 1u) || !(vmax < 0x1p50f) || !(e0 == e0) || !(ex == ex) || !(ey == ey);
         if (bad) {                                   // rare: IEEE intrinsics
             unsigned dummy = 0;
-            e0 = err_from_g1<true>(c, rcp_w, g0, bl, g1a, f.x, f.y, dummy);
-            ex = err_from_g1<true>(c, rcp_w, g0, bl, g1b, fx1, fy1, dummy);
-            ey = err_from_g1<true>(c, rcp_w, g0, bl, g1c, fx2, fy2, dummy);
+            err3_from_g1<true>(c.fw, rcp_w, g0, bl, g1a, g1b, g1c, f.x, f.y, fx1, fy2, ev, dummy);
+            e0 = ev[0]; ex = ev[1]; ey = ev[2];
             q.x = __fdiv_rn(fsub(ex, e0), PF_GRAD_EPS);
             q.y = __fdiv_rn(fsub(ey, e0), PF_GRAD_EPS);
         }

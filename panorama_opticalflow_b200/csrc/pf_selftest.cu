@@ -4,7 +4,7 @@
 
 namespace pf {
 
-// every float bit pattern in the safe range: sqrt_exact_fast(a) must equal __fsqrt_rn(a)
+// every float bit pattern in the safe range: sqrt_exact_fast(a) and sqrt2_exact_fast must equal __fsqrt_rn(a)
 __global__ void k_selftest_sqrt(unsigned long long* mismatches) {
     const unsigned long long n = 1ull << 32;
     unsigned long long bad = 0;
@@ -14,6 +14,9 @@ __global__ void k_selftest_sqrt(unsigned long long* mismatches) {
         if (!(a >= 0.0f) || !in_sqrt_range(a)) continue;
         const float want = __fsqrt_rn(a), got = sqrt_exact_fast(a);
         if (__float_as_uint(want) != __float_as_uint(got)) ++bad;
+        // the packed form the sweep and the record prep use, in both halves (the other half holds an unrelated operand)
+        const float2 p0 = upk(sqrt2_exact_fast(a, 2.0f)), p1 = upk(sqrt2_exact_fast(0.0f, a));
+        if (__float_as_uint(want) != __float_as_uint(p0.x) || __float_as_uint(want) != __float_as_uint(p1.y)) ++bad;
     }
     if (bad) atomicAdd(mismatches, bad);
 }

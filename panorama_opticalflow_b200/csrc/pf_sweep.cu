@@ -182,14 +182,12 @@ __device__ __forceinline__ uint4 ll_load_shared(unsigned saddr) {
 __device__ __forceinline__ void ll_store_shared(unsigned saddr, uint4 v) {
     asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// predicated forms (no branch around the store: the step body is latency-bound)
-__device__ __forceinline__ void ll_store_global_if(bool p, uint4* ptr, uint4 v) {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4}; }"
-                 :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)p) : "memory");
-}
-__device__ __forceinline__ void ll_store_shared_if(bool p, unsigned saddr, uint4 v) {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4}; }"
-                 :: "r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)p) : "memory");
+// The hand-off of a warp's last row: one line {fx, flag, fy, flag}, to the global boundary array (last warp of a CTA) or to the next
+// warp's shared-memory ring.  ONE predicated store through a generic address (the target is a loop invariant of the warp), so that the
+// line is built once; no branch around it (the step body is latency-bound).
+__device__ __forceinline__ void ll_store_generic_if(bool p, unsigned long long addr, uint4 v) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.volatile.v4.u32 [%0], {%1,%2,%3,%4}; }"
+                 :: "l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((unsigned)p) : "memory");
 }
 __device__ __forceinline__ void st_volatile_shared_s32(unsigned saddr, int v) {
     asm volatile("st.volatile.shared.s32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory");
@@ -243,48 +241,19 @@ __device__ __forceinline__ void tma_bulk_g2s(unsigned smem_dst, const void* gmem
 struct SweepConst {
     const float2* G1s;
     unsigned touch;          // this lane's 16-byte scratch slot in shared memory (target of the L1 warm-up copies)
-    int g1s_last, dstep, pitch;
+    int g1s_last, warm, pitch;          // warm: this lane's prefetch offset (elements of G1s ahead of the cell it gathers now)
     float wm2, hm2, fw, rcp_w, rcp_eps;
 };
 
-// The part of errorFunction (CPU/PixFlow.hpp:447-455) after the bilinear gather, with the (x, y) channel pairs on the packed
-// fp32x2 pipe (pf_math.cuh): G1 = (I1x, I1y) at the matched position.  Same operations, same order, same roundings as the
-// scalar form.  The operand keys of the branch-free exact sequences are folded into `tiny` (see tiny_key).
-template <bool SLOW>
-__device__ __forceinline__ float err_tail(const SweepConst& k, f2p G1, float2 g0, float2 bl, float fx, float fy, unsigned& tiny) {
-    const f2p D = psub(pk(bl), pk(fx, fy));
-    const float2 d2 = upk(pmul(D, D));
-    const float ss = fadd(d2.x, d2.y);
-    const f2p E = psub(pk(g0), G1);
-    const float2 e2 = upk(pmul(E, E));
-    const float gs = fadd(e2.x, e2.y);
-    const float ty = fmul(PF_VERT_REG_COEF, fabsf(fy)), tx = fmul(PF_HORZ_REG_COEF, fabsf(fx));
-    float smooth, grad, ry, rx;
-    if (SLOW) {
-        smooth = __fsqrt_rn(ss); grad = __fsqrt_rn(gs);
-        ry = __fdiv_rn(ty, k.fw); rx = __fdiv_rn(tx, k.fw);
-    } else {
-        const float2 sq = upk(sqrt2_exact_fast(ss, gs));
-        smooth = sq.x; grad = sq.y;
-        const float2 rr = upk(div2_by_const(pk(ty, tx), k.fw, k.rcp_w));      // ty, tx >= +0
-        ry = rr.x; rx = rr.y;
-        tiny = min(tiny, min(min(tiny_key(ss), tiny_key(gs)), min(tiny_key(ty), tiny_key(tx))));
-    }
-    float err = fadd(grad, fmul(smooth, PF_SMOOTHNESS_COEF));
-    err = fadd(err, ry);
-    err = fadd(err, rx);
-    return err;
-}
-
 // getPixBilinear32FExtend (CPU/PixFlow.hpp:407-425) on the skewed layout: the clamped cell and the fractional parts
-struct SkewCell { int gi; float xR, yR; };
+struct SkewPos { int gi; float xR, yR; };
 
 template <int POSX>
-__device__ __forceinline__ SkewCell skew_cell(const SweepConst& k, float mxr, float myr) {
+__device__ __forceinline__ SkewPos skew_cell(const SweepConst& k, float mxr, float myr) {
     // fmaxf/fminf == the std::max/std::min of the reference (NaN -> 0 included)
     const float mx = fminf(fmaxf(mxr, 0.0f), k.wm2), my = fminf(fmaxf(myr, 0.0f), k.hm2);
     const int x0 = __float2int_rz(mx), y0 = __float2int_rz(my);
-    SkewCell c;
+    SkewPos c;
     c.xR = fsub(mx, truncf(mx)); c.yR = fsub(my, truncf(my));
     c.gi = (x0 + y0) * k.pitch + (POSX ? x0 : y0);
     return c;
@@ -306,17 +275,14 @@ __device__ __forceinline__ SkewCoef skew_gather(const SweepConst& k, int gi) {
     return c;
 }
 
-template <bool SLOW>
-__device__ __forceinline__ float err_from_taps(const SweepConst& k, const SkewCoef& t, float xR, float yR, float2 g0, float2 bl,
-                                               float fx, float fy, unsigned& tiny) {
-    const f2p G1 = padd(padd(padd(t.f00, pmuls(t.a2, xR)), pmuls(t.a3, yR)), pmuls(pmuls(t.a4, xR), yR));
-    return err_tail<SLOW>(k, G1, g0, bl, fx, fy, tiny);
+__device__ __forceinline__ f2p skew_interp(const SkewCoef& t, float xR, float yR) {
+    return padd(padd(padd(t.f00, pmuls(t.a2, xR)), pmuls(t.a3, yR)), pmuls(pmuls(t.a4, xR), yR));
 }
 
 // warm L1 with the anti-diagonal the gather reaches a few steps from now: an asynchronous 16-byte cp.async.ca into a
 // scratch slot allocates the line in L1 and never blocks (its data is not used)
 __device__ __forceinline__ void warm_gather(const SweepConst& k, int gi) {
-    int pi = gi + 2 * k.pitch + 1 + SW_PREFETCH_GATHER * k.dstep;
+    int pi = gi + k.warm;
     pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
     cp_async16(k.touch, k.G1s + pi);
 }
@@ -330,14 +296,14 @@ __device__ __forceinline__ void eval_probes3(const SweepConst& k, float xf, floa
                                              float v[3], unsigned& tiny) {
     const float fx0 = cand.x, fy0 = cand.y;
     const float fx1 = fadd(cand.x, PF_GRAD_EPS), fy2 = fadd(cand.y, PF_GRAD_EPS);
-    const SkewCell c0 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy0));
-    const SkewCell c1 = skew_cell<POSX>(k, fadd(xf, fx1), fadd(yf, fy0));
-    const SkewCell c2 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy2));
+    const SkewPos c0 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy0));
+    const SkewPos c1 = skew_cell<POSX>(k, fadd(xf, fx1), fadd(yf, fy0));
+    const SkewPos c2 = skew_cell<POSX>(k, fadd(xf, fx0), fadd(yf, fy2));
     const SkewCoef t0 = skew_gather<POSX>(k, c0.gi), t1 = skew_gather<POSX>(k, c1.gi), t2 = skew_gather<POSX>(k, c2.gi);
     if (warm) warm_gather(k, c0.gi);
-    v[0] = err_from_taps<SLOW>(k, t0, c0.xR, c0.yR, g0, bl, fx0, fy0, tiny);
-    v[1] = err_from_taps<SLOW>(k, t1, c1.xR, c1.yR, g0, bl, fx1, fy0, tiny);
-    v[2] = err_from_taps<SLOW>(k, t2, c2.xR, c2.yR, g0, bl, fx0, fy2, tiny);
+    // the part of errorFunction after the gather, for the three probes together (pf_prep.cuh)
+    err3_from_g1<SLOW>(k.fw, k.rcp_w, g0, bl, skew_interp(t0, c0.xR, c0.yR), skew_interp(t1, c1.xR, c1.yR), skew_interp(t2, c2.xR, c2.yR),
+                       fx0, fy0, fx1, fy2, v, tiny);
 }
 
 // One candidate's gradient step (CPU/PixFlow.hpp:321, :364-386) from its three errors {E, E(+dx), E(+dy)}: r = cand - step * dE/eps
@@ -413,7 +379,15 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
     const bool has_out = jw + SW_ROWS < h;                         // warp-uniform
     const bool out_global = wi == SW_WARPS - 1;
     const unsigned rin = pin_i((int)smem_u32(&sm.llring[wi][0]));
-    const unsigned rout = pin_i((int)smem_u32(&sm.llring[(wi + 1) % SW_WARPS][0]));
+    // hand-off target of the warp's last row as one generic address: hbase + (column & hmask) * 16, flag = ((column & emask) / ring) + 1
+    // (global boundary array: no wrap, flag 1; shared ring of the next warp: wraps, flag = lap number)
+    unsigned long long hbase = out_global ? reinterpret_cast<unsigned long long>(a.boundary + (size_t)b * a.s.w)
+                                          : static_cast<unsigned long long>(__cvta_generic_to_shared(&sm.llring[(wi + 1) % SW_WARPS][0]));
+    if (!out_global) {       // shared window -> generic address
+        asm("cvta.shared.u64 %0, %0;" : "+l"(hbase));
+    }
+    hbase = ((unsigned long long)(unsigned)pin_i((int)(hbase >> 32)) << 32) | (unsigned)pin_i((int)(unsigned)hbase);
+    const unsigned hmask = pin_i(out_global ? 0x7fffffff : SW_LL_RING - 1), emask = pin_i(out_global ? 0 : -1);
     const unsigned prog_in = smem_u32(&sm.progress[wi]);
     const unsigned prog_out = smem_u32(&sm.progress[(wi + 1) % SW_WARPS]);
     int out_limit = SW_LL_RING;                                    // columns < out_limit fit in the out ring unchecked
@@ -422,10 +396,12 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
     k.G1s = a.G1s; k.g1s_last = (int)a.g1s_last;
     k.touch = smem_u32(&sm.touch[wi][lane]);
     k.pitch = a.s.pitch;
-    k.dstep = DIR * (k.pitch + POSX);
+    // L1 warm-up of the gather: the third anti-diagonal of the bilinear cell, SW_PREFETCH_GATHER steps ahead on lane 0 of a row and
+    // twice as far on lane 1 (the near one catches what the far one mispredicted or lost: 40.2 -> 38.9 ms for one 4000 x 2000 pair)
+    k.warm = 2 * k.pitch + 1 + SW_PREFETCH_GATHER * DIR * (k.pitch + POSX) * (1 + sub);
     k.wm2 = fsub((float)w, 2.0f); k.hm2 = fsub((float)h, 2.0f); k.fw = (float)w;
     k.rcp_w = __frcp_rn(k.fw); k.rcp_eps = __frcp_rn(PF_GRAD_EPS);
-    w = pin_i(w); k.pitch = pin_i(k.pitch); k.dstep = pin_i(k.dstep); k.g1s_last = pin_i(k.g1s_last); k.touch = pin_i(k.touch);
+    w = pin_i(w); k.pitch = pin_i(k.pitch); k.warm = pin_i(k.warm); k.g1s_last = pin_i(k.g1s_last); k.touch = pin_i(k.touch);
     k.wm2 = pin_f(k.wm2); k.hm2 = pin_f(k.hm2); k.fw = pin_f(k.fw); k.rcp_w = pin_f(k.rcp_w); k.rcp_eps = pin_f(k.rcp_eps);
     {
         unsigned long long p = reinterpret_cast<unsigned long long>(k.G1s);
@@ -438,7 +414,6 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
     float xf = (float)(DIR > 0 ? -g : w - 1 + g);                  // float(x) of step 0, then +-1 per step (exact)
     int i = rowValid ? -g : -0x40000000;                           // logical column of this row, +1 per step; rows past h never become valid
     float2* fptr = a.flow + (size_t)y * a.fp + (DIR > 0 ? -g : w - 1 + g);          // &flow(y, x) of the current step (dereferenced only where valid)
-    uint4* gptr = a.boundary + (size_t)b * w - (SW_ROWS - 1);      // &boundary line of the last row's column (i_last = s - 15)
 
     // ---- record stream: 512 bytes per step, 4 steps per TMA bulk copy, SW_NSTAGES stages, fed by this warp's lane 0 ----
     const int nstages = sweep_nsteps_pad_dev(w) / SW_STAGE_STEPS;
@@ -464,7 +439,7 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
     const int in_cols = has_in ? w : 0;           // columns to take from the inbound ring
     const bool ring_out = has_out && !out_global;
     const bool last_row = lane == 2 * (SW_ROWS - 1);               // lane 0 of the warp's last row
-    const bool st_glob = has_out && out_global && last_row, st_ring = ring_out && last_row;
+    const bool st_out = has_out && last_row;
     const bool storer = sub == 0;
     int s = 0;                                    // wavefront step
 
@@ -480,6 +455,10 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
 
     for (int t = 0; t < nstages; ++t) {
         const unsigned srec = my_rec + (t % SW_NSTAGES) * SW_STAGE_BYTES;
+        // back-pressure, once per stage (rare): the out ring must have room for the columns this stage hands down, s - 15 .. s - 15 + 3
+        // (the consumer publishes its progress at its own stage ends and can always consume what has been handed down so far)
+        if (ring_out)
+            while (s + SW_STAGE_STEPS - SW_ROWS >= out_limit) out_limit = ld_volatile_shared_s32(prog_out) + SW_LL_RING;
 #pragma unroll
         for (int u = 0; u < SW_STAGE_STEPS; ++u, ++s) {
             // steps past w + 14 (padding of the last stage) have no valid pixel and fall through the skip below
@@ -496,13 +475,14 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
                 float2 up;
                 up.x = __shfl_up_sync(full, res.x, 2);
                 up.y = __shfl_up_sync(full, res.y, 2);
-                if (s < in_cols) {                        // warp-uniform: every lane reads the same ring entry
+                {   // warp-uniform: every lane reads the same ring entry (columns past in_cols: read, not waited for, not used)
+                    const bool need = s < in_cols;
                     const unsigned e = ((unsigned)s / SW_LL_RING) + 1u;
                     const unsigned ra = rin + ((unsigned)s & (SW_LL_RING - 1)) * 16u;
-                    uint4 v = ll_load_shared(ra);
-                    while (v.y != e || v.w != e) v = ll_load_shared(ra);
-                    up.x = g == 0 ? __uint_as_float(v.x) : up.x;
-                    up.y = g == 0 ? __uint_as_float(v.z) : up.y;
+                    uint4 v;
+                    do { v = ll_load_shared(ra); } while (need && (v.y != e || v.w != e));
+                    up.x = (need && g == 0) ? __uint_as_float(v.x) : up.x;
+                    up.y = (need && g == 0) ? __uint_as_float(v.z) : up.y;
                 }
                 const float2 g0 = make_float2(B.x, B.y), bl = make_float2(B.z, B.w);
                 const float2 cand = make_float2(sub ? up.x : res.x, sub ? up.y : res.y);
@@ -533,17 +513,13 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
             if (active && storer) *fptr = out;
             {
                 const int i_last = s - (SW_ROWS - 1);                 // column of the warp's last row (warp-uniform)
-                if (ring_out && i_last >= out_limit)                  // back-pressure, rare: wait until the slot is free
-                    while (i_last >= out_limit) out_limit = ld_volatile_shared_s32(prog_out) + SW_LL_RING;
-                const unsigned e = out_global ? 1u : ((unsigned)i_last / SW_LL_RING) + 1u;
+                const unsigned e = (((unsigned)i_last & emask) / SW_LL_RING) + 1u;
                 const uint4 lv = make_uint4(__float_as_uint(out.x), e, __float_as_uint(out.y), e);
-                ll_store_global_if(st_glob && valid, gptr, lv);
-                ll_store_shared_if(st_ring && valid, rout + ((unsigned)i_last & (SW_LL_RING - 1)) * 16u, lv);
+                ll_store_generic_if(st_out && valid, hbase + (unsigned long long)((unsigned)i_last & hmask) * 16ull, lv);
             }
             xf = fadd(xf, (float)DIR);
             ++i;
             fptr += DIR;
-            ++gptr;
         }
         // ---- stage boundary: every lane holds its last records of stage t in registers ----
         __syncwarp();
