@@ -452,6 +452,7 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
     float4 A, B;
     mbar_wait(full0, 0);
     load_rec(my_rec, A, B);
+    uint4 rv = ll_load_shared(rin);
 
     for (int t = 0; t < nstages; ++t) {
         const unsigned srec = my_rec + (t % SW_NSTAGES) * SW_STAGE_BYTES;
@@ -479,8 +480,8 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
                     const bool need = s < in_cols;
                     const unsigned e = ((unsigned)s / SW_LL_RING) + 1u;
                     const unsigned ra = rin + ((unsigned)s & (SW_LL_RING - 1)) * 16u;
-                    uint4 v;
-                    do { v = ll_load_shared(ra); } while (need && (v.y != e || v.w != e));
+                    uint4 v = rv;                                  // fetched at the end of the previous step (38.2 -> 37.5 ms per pair)
+                    while (need && (v.y != e || v.w != e)) v = ll_load_shared(ra);
                     up.x = (need && g == 0) ? __uint_as_float(v.x) : up.x;
                     up.y = (need && g == 0) ? __uint_as_float(v.z) : up.y;
                 }
@@ -495,18 +496,23 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
                 const bool bad = tkey < PF_TINY_BITS - 1u || !(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fabsf(v[2])) < 0x1p50f);
                 float eM = v[0];
                 float eO = oe;
-                if (__any_sync(full, bad && active)) {                     // rare: redo with the IEEE intrinsics, out of line
+                // the pair exchanges its finished candidates and selects BEFORE the range check of the branch-free sequences is known
+                // (vote + branch off the dependent chain); the rare redo with the IEEE intrinsics repeats exchange and select
+                float2 other = make_float2(__shfl_xor_sync(full, mine.x, 1), __shfl_xor_sync(full, mine.y, 1));
+                if (u + 1 < SW_STAGE_STEPS) load_rec(srec + (u + 1) * STEP_BYTES, A, B);      // records of the next step
+                out = select_result(sub ? eO : eM, sub ? other : mine, sub ? eM : eO, sub ? mine : other, i > 0, j > 0, Ac);
+                if (__any_sync(full, bad && active)) {                     // out of line
                     const float4 sl = step_slow<POSX>(k, xf, yf, g0, bl, cand);
                     eM = sl.x; mine = make_float2(sl.y, sl.z);
                     eO = __shfl_xor_sync(full, eM, 1);
+                    other = make_float2(__shfl_xor_sync(full, mine.x, 1), __shfl_xor_sync(full, mine.y, 1));
+                    out = select_result(sub ? eO : eM, sub ? other : mine, sub ? eM : eO, sub ? mine : other, i > 0, j > 0, Ac);
                 }
-                const float2 other = make_float2(__shfl_xor_sync(full, mine.x, 1), __shfl_xor_sync(full, mine.y, 1));
-                // ---- records of the next step (same stage: the address is a compile-time offset) ----
-                if (u + 1 < SW_STAGE_STEPS) load_rec(srec + (u + 1) * STEP_BYTES, A, B);
-                out = select_result(sub ? eO : eM, sub ? other : mine, sub ? eM : eO, sub ? mine : other, i > 0, j > 0, Ac);
             } else {
                 if (u + 1 < SW_STAGE_STEPS) load_rec(srec + (u + 1) * STEP_BYTES, A, B);
             }
+            // the ring entry of the next step, early: when the upstream warp is a step ahead it is valid already and the wait below never loads
+            if (u + 1 < SW_STAGE_STEPS) rv = ll_load_shared(rin + ((unsigned)(s + 1) & (SW_LL_RING - 1)) * 16u);
             res.x = valid ? out.x : res.x;
             res.y = valid ? out.y : res.y;
             // ---- results: flow (row-major, only where alpha > 0.9) and the hand-off of the warp's last row ----
@@ -535,6 +541,7 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
             const int sn = (t + 1) % SW_NSTAGES;
             mbar_wait(full0 + sn * 8, ((t + 1) / SW_NSTAGES) & 1);
             load_rec(my_rec + sn * SW_STAGE_BYTES, A, B);
+            rv = ll_load_shared(rin + ((unsigned)s & (SW_LL_RING - 1)) * 16u);
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
