@@ -197,6 +197,23 @@ __device__ __forceinline__ int ld_volatile_shared_s32(unsigned saddr) {
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+// Waits until the LL line at `saddr` carries flag e in both halves; v holds a copy read earlier.  Every lane of the warp reads the SAME
+// line, so the loop is warp-uniform: bra.uni tells the assembler so (no convergence barriers around the common, already-valid case).
+__device__ __forceinline__ void ll_wait_shared_uniform(uint4& v, unsigned saddr, unsigned e, bool need) {
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "setp.ne.u32 p, %1, %5;\n\t"
+                 "setp.ne.or.u32 p, %3, %5, p;\n\t"
+                 "setp.ne.and.u32 p, %6, 0, p;\n\t"
+                 "@!p bra.uni LL_DONE;\n\t"
+                 "LL_SPIN:\n\t"
+                 "ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t"
+                 "setp.ne.u32 p, %1, %5;\n\t"
+                 "setp.ne.or.u32 p, %3, %5, p;\n\t"
+                 "@p bra.uni LL_SPIN;\n\t"
+                 "LL_DONE:\n\t"
+                 "}" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "r"(saddr), "r"(e), "r"((unsigned)need) : "memory");
+}
 // the exchange words {error bits, tag}: one 8-byte scalar access each (single-copy atomic)
 __device__ __forceinline__ void xchg_store(unsigned saddr, float e, unsigned tag) {
     asm volatile("st.volatile.shared.v2.u32 [%0], {%1,%2};" :: "r"(saddr), "r"(__float_as_uint(e)), "r"(tag) : "memory");
@@ -252,8 +269,8 @@ template <int POSX>
 __device__ __forceinline__ SkewPos skew_cell(const SweepConst& k, float mxr, float myr) {
     // fmaxf/fminf == the std::max/std::min of the reference (NaN -> 0 included)
     const float mx = fminf(fmaxf(mxr, 0.0f), k.wm2), my = fminf(fmaxf(myr, 0.0f), k.hm2);
-    const int x0 = __float2int_rz(mx), y0 = __float2int_rz(my);
     SkewPos c;
+    const int x0 = __float2int_rz(mx), y0 = __float2int_rz(my);
     c.xR = fsub(mx, truncf(mx)); c.yR = fsub(my, truncf(my));
     c.gi = (x0 + y0) * k.pitch + (POSX ? x0 : y0);
     return c;
@@ -481,7 +498,7 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
                     const unsigned e = ((unsigned)s / SW_LL_RING) + 1u;
                     const unsigned ra = rin + ((unsigned)s & (SW_LL_RING - 1)) * 16u;
                     uint4 v = rv;                                  // fetched at the end of the previous step (38.2 -> 37.5 ms per pair)
-                    while (need && (v.y != e || v.w != e)) v = ll_load_shared(ra);
+                    ll_wait_shared_uniform(v, ra, e, need);
                     up.x = (need && g == 0) ? __uint_as_float(v.x) : up.x;
                     up.y = (need && g == 0) ? __uint_as_float(v.z) : up.y;
                 }
