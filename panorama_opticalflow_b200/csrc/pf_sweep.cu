@@ -415,7 +415,7 @@ __device__ __forceinline__ void sweep_rows(const Sweep2Args& a, SweepSmem& sm, c
     k.pitch = a.s.pitch;
     // L1 warm-up of the gather: the third anti-diagonal of the bilinear cell, SW_PREFETCH_GATHER steps ahead on lane 0 of a row and
     // twice as far on lane 1 (the near one catches what the far one mispredicted or lost: 40.2 -> 38.9 ms for one 4000 x 2000 pair)
-    k.warm = 2 * k.pitch + 1 + SW_PREFETCH_GATHER * DIR * (k.pitch + POSX) * (1 + sub);
+        k.warm = 2 * k.pitch + 1 + SW_PREFETCH_GATHER * DIR * (k.pitch + POSX) * (1 + sub);
     k.wm2 = fsub((float)w, 2.0f); k.hm2 = fsub((float)h, 2.0f); k.fw = (float)w;
     k.rcp_w = __frcp_rn(k.fw); k.rcp_eps = __frcp_rn(PF_GRAD_EPS);
     w = pin_i(w); k.pitch = pin_i(k.pitch); k.warm = pin_i(k.warm); k.g1s_last = pin_i(k.g1s_last); k.touch = pin_i(k.touch);
