@@ -117,6 +117,12 @@ struct Workspace {
     float* blend = nullptr;
     cudaStream_t sMain = nullptr, sDir[2] = {nullptr, nullptr};
     cudaEvent_t evReady = nullptr, evDone[2] = {nullptr, nullptr};
+    // Latency flavour (a pair alone on the device): the gradient pyramids are built on a third stream, coarsest level first, while the
+    // directions already work on the coarse levels -- evPyr: image pyramids complete, evG[l]: gradients of level l (both images) complete
+    cudaStream_t sAux = nullptr;
+    cudaEvent_t evPyr = nullptr;
+    std::vector<cudaEvent_t> evG;
+    bool overlap_front = false;                   // for the next enqueue
     cudaEvent_t evIn = nullptr;                   // host inputs staged (recorded on the engine's copy stream)
     cudaEvent_t evOut = nullptr;                  // host outputs copied back (recorded on the engine's download stream)
     bool outPending = false;                      // evOut must be waited for before the results are complete
@@ -128,7 +134,7 @@ struct Workspace {
     // with a single launch: ~1000 kernel launches per pair would otherwise cost ~3 ms of host time each call
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_launches = 0;                  // kernels per replay
-    int graph_key = -1;                           // ndir | hint0 << 4 | hint1 << 8 | search_dist << 12 | sweep_cta_divisor << 20
+    int graph_key = -1;                           // ndir | hint0 << 4 | hint1 << 8 | search_dist << 12 | sweep_cta_divisor << 20 | overlap_front << 28
     int sweep_cta_divisor = 1;                    // for the next enqueue: 1 latency flavour, > 1 throughput flavour (launch_sweep2)
 
     ~Workspace() { release(); }
@@ -150,6 +156,11 @@ struct Workspace {
         cudaFree(Ipre); cudaFree(merged); cudaFree(blend);
         Ipre = nullptr; merged = nullptr; blend = nullptr;
         if (evReady) cudaEventDestroy(evReady);
+        if (evPyr) cudaEventDestroy(evPyr);
+        for (auto e : evG) cudaEventDestroy(e);
+        evG.clear();
+        if (sAux) cudaStreamDestroy(sAux);
+        sAux = nullptr; evPyr = nullptr;
         if (evIn) cudaEventDestroy(evIn);
         if (evOut) cudaEventDestroy(evOut);
         if (evNovel) cudaEventDestroy(evNovel);
@@ -205,6 +216,10 @@ struct Workspace {
         PF_CUDA(cudaMalloc(&Ipre, px0 * sizeof(float)));
         sMain = sDir[0];   // the shared front end runs on direction 0's stream: two streams (hardware queues) per pair
         PF_CUDA(cudaEventCreateWithFlags(&evReady, cudaEventDisableTiming));
+        PF_CUDA(cudaEventCreateWithFlags(&evPyr, cudaEventDisableTiming));
+        PF_CUDA(cudaStreamCreateWithFlags(&sAux, cudaStreamNonBlocking));
+        evG.resize(plan.L);
+        for (auto& ev : evG) PF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         PF_CUDA(cudaEventCreateWithFlags(&evIn, cudaEventDisableTiming));
         PF_CUDA(cudaEventCreateWithFlags(&evOut, cudaEventDisableTiming));
         PF_CUDA(cudaEventCreateWithFlags(&evNovel, cudaEventDisableTiming));
@@ -296,6 +311,22 @@ int enqueue_shared(pf_engine* e, Workspace& w, const uint8_t* img[2], const size
         pf::launch_pyr_down(ps, 4, p.hs[l - 1], p.ws[l - 1], p.hs[l], p.ws[l], w.sMain);
         LAUNCHED(1);
     }
+    if (w.overlap_front) {
+        // gradients on their own stream, coarsest level first: the directions start as soon as the coarsest level's are there and
+        // the rest (90 % of the gradient work) runs under the coarse levels' sweeps, which leave the device almost empty
+        PF_CUDA(cudaEventRecord(w.evPyr, w.sMain));
+        PF_CUDA(cudaStreamWaitEvent(w.sAux, w.evPyr, 0));
+        for (int l = p.L - 1; l >= 0; --l) {
+            for (int k = 0; k < 2; ++k) {
+                pf::launch_gradient(w.I[k] + p.off[l], w.G[k] + p.off[l], p.hs[l], p.ws[l], w.sAux);
+                pf::launch_skew_copy_f2(w.G[k] + p.off[l], w.Gs[k] + p.skew_off[l], p.skew[l], w.sAux);
+                LAUNCHED(2);
+            }
+            PF_CUDA(cudaEventRecord(w.evG[l], w.sAux));
+        }
+        PF_CUDA(cudaGetLastError());
+        return PF_OK;
+    }
     for (int l = 0; l < p.L; ++l)
         for (int k = 0; k < 2; ++k) {
             pf::launch_gradient(w.I[k] + p.off[l], w.G[k] + p.off[l], p.hs[l], p.ws[l], w.sMain);
@@ -312,13 +343,14 @@ int enqueue_direction(pf_engine* e, Workspace& w, int d, int i0, int hint, float
     const Plan& p = w.plan;
     const int i1 = 1 - i0;
     cudaStream_t st = w.sDir[d];
-    PF_CUDA(cudaStreamWaitEvent(st, w.evReady, 0));
+    PF_CUDA(cudaStreamWaitEvent(st, w.overlap_front ? w.evPyr : w.evReady, 0));
     PF_CUDA(cudaMemsetAsync(w.bnd[d], 0, (p.bnd_lines + 1) * sizeof(uint4), st));
     PF_CUDA(cudaMemsetAsync(w.tickets[d], 0, (size_t)p.L * 2 * sizeof(int), st));
     float2* flow = w.bufA[d];
     float2* other = w.bufB[d];
     for (int l = p.L - 1; l >= 0; --l) {
         const int h = p.hs[l], wd = p.ws[l], fp = pf::flow_pitch(wd);
+        if (w.overlap_front) PF_CUDA(cudaStreamWaitEvent(st, w.evG[l], 0));
         const float* I0 = w.I[i0] + p.off[l];
         const float* I1 = w.I[i1] + p.off[l];
         const float* A0 = w.A[i0] + p.off[l];
@@ -431,7 +463,7 @@ int enqueue_pair(pf_engine* e, Workspace& w, const void* imgL, size_t strideL, c
             PF_CUDA(cudaEventRecord(w.evIn, e->sCopy));
             PF_CUDA(cudaStreamWaitEvent(st, w.evIn, 0));
         }
-        const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12) | (w.sweep_cta_divisor << 20);
+        const int key = ndir | (hints[0] << 4) | (hints[1] << 8) | (e->search_dist << 12) | (w.sweep_cta_divisor << 20) | ((int)w.overlap_front << 28);
         bool have_graph = w.graph_key == key;
         if (!have_graph) {
             std::lock_guard<std::mutex> cg(g_capture_mu);
@@ -639,6 +671,7 @@ int pf_timer_stop(pf_engine* e, double* ms) {
 }
 
 static int wait_slot_locked(pf_engine* e, int slot);
+static bool front_overlap_for_pairs(int n);
 
 int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, size_t s1, int rows, int cols, int hint,
                     void* flow_out, size_t flow_stride) {
@@ -655,6 +688,7 @@ int pf_compute_flow(pf_engine* e, const void* i0, size_t s0, const void* i1, siz
     if ((rc = wait_slot_locked(e, 0)) != PF_OK) return rc;        // an asynchronous batch may still own workspace 0
     if ((rc = e->workspace(0, rows, cols, 0, &w)) != PF_OK) return rc;
     w->sweep_cta_divisor = 1;
+    w->overlap_front = front_overlap_for_pairs(1);
     const int hints[2] = {hint, 0};
     void* outs[2] = {flow_out, nullptr};
     const size_t ostr[2] = {flow_stride, 0};
@@ -678,6 +712,16 @@ static int sweep_cta_divisor_for_pairs(int n) {
         if (div < 1 || div > 16) div = 1;
     }
     return n <= max_pairs ? 1 : div;
+}
+// the same switch-over for the overlapped gradient chain (Workspace::overlap_front); PF_NO_FRONT_OVERLAP=1 turns it off
+static bool front_overlap_for_pairs(int n) {
+    static int max_pairs = -1;
+    if (max_pairs < 0) {
+        const char* a = getenv("PF_LATENCY_MAX_PAIRS");
+        const char* off = getenv("PF_NO_FRONT_OVERLAP");
+        max_pairs = (off && atoi(off) != 0) ? 0 : (a ? atoi(a) : 2);
+    }
+    return n <= max_pairs;
 }
 
 // workspace index of pair i of slot s: the two slots own disjoint workspaces (streams, graphs, staging and output buffers)
@@ -705,6 +749,7 @@ static int batch_enqueue_locked(pf_engine* e, int slot, int n, const void* const
         if ((rc = e->workspace(ws_index(slot, i), rows, cols, pad, &w)) != PF_OK) return rc;
         e->inflight[slot].push_back(w);
         w->sweep_cta_divisor = sweep_cta_divisor_for_pairs(n);
+        w->overlap_front = front_overlap_for_pairs(n);
         void* outs[2] = {lr[i], rl[i]};
         const size_t ostr[2] = {slr, srl};
         const uint8_t* dimg[2]; size_t dstr[2]; float2* dflow[2]; size_t dfs[2];
@@ -850,6 +895,7 @@ static int novel_view_locked(pf_engine* e, const void* L, size_t sl, const void*
     if ((rc = wait_slot_locked(e, 0)) != PF_OK) return rc;
     if ((rc = e->workspace(0, rows, cols, pad, &w)) != PF_OK) return rc;
     w->sweep_cta_divisor = 1;
+    w->overlap_front = front_overlap_for_pairs(1);
     w->preWait = inputs_ready;
     const int hints[2] = {PF_HINT_LEFT, PF_HINT_RIGHT};
     void* outs[2] = {lr, rl};
