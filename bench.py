@@ -534,7 +534,9 @@ def run_b200(args, rank, world, local_rank):
                 "api": "pf_prepare_bidirectional_batch_async + pf_wait, two slots: every step uploads its %d image pairs from pinned host memory "
                        "and downloads its %d flow fields; copies of consecutive steps overlap compute" % (B, 2 * B),
                 "sync_api_value": mpix_step / (sync_ms / 1e3), "sync_api_ms_per_step": sync_ms,
-                "fraction_of_device_resident_value": e2e_value / value},
+                "fraction_of_device_resident_value": e2e_value / value,
+                "note": "beyond one GPU the step is bounded by the box's host <-> device copy bandwidth (D2H into host memory stops scaling at "
+                        "two GPUs; at 8 GPUs one step's copies alone take as long as the e2e step: profiles/r2_pcie_probe_n8.md)"},
         "gpu_launches": int(launches) * world, "clocks": clocks,
     }
     emit(line)
