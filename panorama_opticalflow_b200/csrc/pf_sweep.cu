@@ -25,10 +25,12 @@
 //     each, finishes BOTH candidates' gradient steps and then does the reference's two compares.
 //
 // Lanes: two lanes per row (16 rows per warp).  Lane 0 of a pair evaluates the LEFT candidate's three probes, lane 1 the UP
-// candidate's; each finishes its candidate's gradient step and the pair swaps {E, r} with two shuffles.  (Spreading the probes
-// over more lanes or over several warps was measured and is slower: profiles/r2_sweep_v10_experiment.md -- a warp of this
-// kernel retires ~1 instruction per 3.3 cycles whatever the ILP, so only the instruction count per warp-step matters, and a
-// shared-memory exchange between warps costs more dead time than it saves.)
+// candidate's; each finishes its candidate's gradient step and the pair swaps {E, r} with three shuffles.  The step is bound by the
+// LATENCY of its dependent chain (ring / shuffle in -> clamp, floor, address -> L1 gather -> bilinear -> exact square roots -> sums ->
+// exact division -> exchange -> select), not by its instruction count (profiles/r2_sweep_v12_ncu.md): what pays is a shorter chain and
+// fewer L1 misses of the gather, not fewer instructions in the chain's shadow.  Spreading the probes over more lanes (eight lanes per
+// row, one probe each) or over several warps was built and measured and is not faster: the parts of the step without any parallelism
+// (the way in, the exchange, the select, the votes) are the same (profiles/r2_notes.md, profiles/r2_sweep_v10_experiment.md).
 //   * the (x, y) channel pairs of gradients and flows go through Blackwell's packed fp32x2 pipe (FFMA2 / FADD2,
 //     pf_math.cuh): bit-identical to the scalar operations, half the instructions.
 //   * the step body is branch-free: the IEEE divisions (by eps and by cols, both loop-invariant) and square roots
