@@ -299,7 +299,9 @@ __device__ __forceinline__ f2p skew_interp(const SkewCoef& t, float xR, float yR
 }
 
 // warm L1 with the anti-diagonal the gather reaches a few steps from now: an asynchronous 16-byte cp.async.ca into a
-// scratch slot allocates the line in L1 and never blocks (its data is not used)
+// scratch slot allocates the line in L1 and never blocks (its data is not used).  The skewed array has holes that no pixel maps to;
+// a warm-up copy may read them (compute-sanitizer --tool initcheck reports exactly these reads and nothing else): the bytes go to
+// the scratch slot and are never looked at.
 __device__ __forceinline__ void warm_gather(const SweepConst& k, int gi) {
     int pi = gi + k.warm;
     pi = max(0, min(pi, k.g1s_last - 1)) & ~1;
